@@ -1,0 +1,217 @@
+// common.cuh -- shared device/host helpers for libbce_gpu (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bce_gpu.h"
+
+namespace bce {
+
+constexpr int kSMsB200 = 148;
+
+// ---------------------------------------------------------------------------------
+// host side: error plumbing and a grow-only device buffer
+// ---------------------------------------------------------------------------------
+struct Ctx;
+void set_error(Ctx* c, const char* fmt, ...);
+
+#define BCE_CUDA(ctx, call)                                                         \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      bce::set_error((ctx), "%s:%d %s -> %s", __FILE__, __LINE__, #call,            \
+                     cudaGetErrorString(e__));                                      \
+      return (e__ == cudaErrorMemoryAllocation) ? BCE_GPU_E_NOMEM : BCE_GPU_E_CUDA; \
+    }                                                                               \
+  } while (0)
+
+#define BCE_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != BCE_GPU_OK) return rc__; \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(Ctx* c, size_t bytes);   // grow-only; contents are not preserved on growth
+  void release();
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(Ctx* c, size_t bytes);
+  void release();
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// carve aligned pieces out of one scratch allocation
+struct Carver {
+  char* base;
+  size_t off = 0, cap;
+  Carver(void* b, size_t c) : base(reinterpret_cast<char*>(b)), cap(c) {}
+  template <class T> T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    if (off + bytes > cap) { off = cap + 1; return nullptr; }
+    T* r = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+  static size_t need(size_t count, size_t elem) { return (count * elem + 255) & ~size_t(255); }
+};
+
+struct StageTimer {   // CUDA-event stopwatch on the context stream, accumulates into a float
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+
+// ---------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// Tagged tile descriptors for single-pass chained scans (decoupled look-back).
+// word = [ tag:30 | status:2 | value:32 ]; a word whose tag differs from the current
+// pass/round tag is "not written yet", so the arrays never need clearing between passes.
+constexpr uint32_t kDescAgg = 1, kDescPrefix = 2;
+__device__ __forceinline__ uint64_t desc_pack(uint32_t tag, uint32_t status, uint32_t value) {
+  return (uint64_t(tag & 0x3FFFFFFFu) << 34) | (uint64_t(status) << 32) | value;
+}
+__device__ __forceinline__ uint32_t desc_tag(uint64_t w) { return uint32_t(w >> 34); }
+__device__ __forceinline__ uint32_t desc_status(uint64_t w) { return uint32_t(w >> 32) & 3u; }
+__device__ __forceinline__ void desc_store(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_load(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Spin until the descriptor carries `tag`.  The budget bounds the wait so that a logic
+// error surfaces as BCE_GPU_E_INTERNAL instead of a hung GPU.
+constexpr uint32_t kSpinBudget = 1u << 24;
+__device__ __forceinline__ uint64_t desc_wait(const uint64_t* p, uint32_t tag, uint32_t* err) {
+  uint64_t w = desc_load(p);
+  uint32_t spins = 0;
+  while (desc_tag(w) != (tag & 0x3FFFFFFFu)) {
+    if (++spins > kSpinBudget) {
+      atomicExch(err, 1u);
+      return desc_pack(tag, kDescPrefix, 0);
+    }
+    __nanosleep(32);
+    w = desc_load(p);
+  }
+  return w;
+}
+
+// Serial look-back by one thread (used where 256 threads each chase their own digit).
+// Returns the exclusive prefix of `agg` over tiles [0, tile) and publishes the inclusive one.
+__device__ __forceinline__ uint32_t lookback_serial(uint64_t* desc, uint32_t stride, uint32_t tile,
+                                                    uint32_t tag, uint32_t agg, uint32_t* err) {
+  if (tile == 0) {
+    desc_store(desc, desc_pack(tag, kDescPrefix, agg));
+    return 0;
+  }
+  desc_store(desc + size_t(tile) * stride, desc_pack(tag, kDescAgg, agg));
+  uint32_t excl = 0;
+  for (uint32_t t = tile; t-- > 0;) {
+    uint64_t w = desc_wait(desc + size_t(t) * stride, tag, err);
+    excl += uint32_t(w);
+    if (desc_status(w) == kDescPrefix) break;
+  }
+  desc_store(desc + size_t(tile) * stride, desc_pack(tag, kDescPrefix, excl + agg));
+  return excl;
+}
+
+// Same, for the "most recent non-zero value" operator (carry of the last group head).
+__device__ __forceinline__ uint32_t lookback_serial_last(uint64_t* desc, uint32_t stride, uint32_t tile,
+                                                         uint32_t tag, uint32_t agg, uint32_t* err) {
+  if (tile == 0) {
+    desc_store(desc, desc_pack(tag, kDescPrefix, agg));
+    return 0;
+  }
+  // a tile that contains a head already knows its inclusive value
+  desc_store(desc + size_t(tile) * stride, desc_pack(tag, agg ? kDescPrefix : kDescAgg, agg));
+  uint32_t excl = 0;
+  for (uint32_t t = tile; t-- > 0;) {
+    uint64_t w = desc_wait(desc + size_t(t) * stride, tag, err);
+    if (uint32_t(w) != 0) { excl = uint32_t(w); break; }
+    if (desc_status(w) == kDescPrefix) break;
+  }
+  if (!agg) desc_store(desc + size_t(tile) * stride, desc_pack(tag, kDescPrefix, excl));
+  return excl;
+}
+
+// Warp-wide look-back over a chain of tiles [first, tile): all 32 lanes must call it.
+// Returns (to every lane) the exclusive prefix and publishes the inclusive one.
+__device__ __forceinline__ uint32_t lookback_warp(uint64_t* desc, uint32_t tile, uint32_t first,
+                                                  uint32_t tag, uint32_t agg, uint32_t* err) {
+  const unsigned lane = lane_id();
+  if (tile == first) {
+    if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescPrefix, agg));
+    return 0;
+  }
+  if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescAgg, agg));
+  uint32_t excl = 0;
+  int64_t base = int64_t(tile) - 1;
+  for (;;) {
+    int64_t t = base - lane;
+    bool inside = t >= int64_t(first);
+    uint64_t w = inside ? desc_wait(desc + t, tag, err) : desc_pack(tag, kDescPrefix, 0);
+    unsigned pm = __ballot_sync(0xffffffffu, desc_status(w) == kDescPrefix);
+    uint32_t v = uint32_t(w);
+    if (pm) {
+      unsigned stop = __ffs(pm) - 1;           // nearest predecessor with a full prefix
+      if (lane > stop) v = 0;
+      excl += __reduce_add_sync(0xffffffffu, v);
+      break;
+    }
+    excl += __reduce_add_sync(0xffffffffu, v);
+    base -= 32;
+  }
+  if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescPrefix, excl + agg));
+  return excl;
+}
+
+// Block-wide exclusive scan of one value per thread (THREADS multiple of 32, <= 1024).
+// `total` receives the block sum.  Uses (THREADS/32) words of shared scratch.
+template <class T, int THREADS>
+__device__ __forceinline__ T block_exclusive_scan(T v, T* scratch, T& total) {
+  constexpr int NW = THREADS / 32;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  T inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    T o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= unsigned(d)) inc += o;
+  }
+  if (lane == 31) scratch[warp] = inc;
+  __syncthreads();
+  T woff = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    T s = scratch[w];
+    if (unsigned(w) < warp) woff += s;
+    tot += s;
+  }
+  __syncthreads();          // scratch may be reused right after
+  total = tot;
+  return woff + inc - v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace bce

@@ -1,0 +1,92 @@
+// ctx.h -- the context behind bce_gpu_ctx and the internal stage entry points.
+#pragma once
+
+#include "common.cuh"
+
+struct bce_gpu_ctx {};   // opaque to callers; bce::Ctx derives from it
+
+namespace bce {
+
+constexpr int kMaxSortRounds = 48;
+
+struct CseDeviceState;   // cse.cu
+
+struct Ctx : bce_gpu_ctx {
+  int device = 0;
+  int sm_count = 0;
+  size_t total_mem = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  char err[512] = {0};
+  size_t scratch_limit = 0;
+
+  // persistent device data
+  DevBuf text;        // T, padded (n + 64)
+  DevBuf bwt;         // L, padded
+  DevBuf ranks;       // 8 x rank_words u64
+  DevBuf scratch;     // carved per stage
+  DevBuf small;       // counters, histograms, descriptors' tickets, state structs
+  DevBuf desc;        // tile descriptors (tagged, never cleared between passes)
+  PinnedBuf pinned_small;   // host mirror for small read-backs
+  PinnedBuf pinned_emit;    // emitted counts handed to the caller
+  PinnedBuf pinned_io;      // staging for pageable caller buffers
+
+  uint32_t desc_tag = 0;    // monotonically increasing pass tag (30 bits used)
+
+  // state of the current input
+  uint32_t n = 0;
+  bool text_resident = false;
+  bool bwt_resident = false;
+  bool ranks_resident = false;
+  uint32_t offset = 0;
+  uint32_t C[8] = {};
+
+  // CSE run state (host side)
+  bool cse_active = false;
+  bool cse_done = false;
+  struct CseHost* cse = nullptr;
+
+  bce_gpu_stats stats = {};
+};
+
+// layout of Ctx::small (device) in bytes; Ctx::pinned_small mirrors it on the host
+constexpr size_t kSmallHist = 0;                              // 8 x 256 u32  digit histograms
+constexpr size_t kSmallBase = kSmallHist + 8 * 256 * 4;       // 8 x 256 u32  digit starts
+constexpr size_t kSmallTicket = kSmallBase + 8 * 256 * 4;     // 16 u32       radix tile dispensers
+constexpr size_t kSmallErr = kSmallTicket + 64;               // 1 u32        chained-scan watchdog flag
+constexpr size_t kSmallRerankTicket = kSmallErr + 64;         // 1 u32
+constexpr size_t kSmallRerankTotals = kSmallRerankTicket + 64;  // 2 u32
+constexpr size_t kSmallWavelet = kSmallRerankTotals + 64;     // 256 u32 hist + 8 u32 zeros + 8 tickets
+constexpr size_t kSmallCse = kSmallWavelet + 2048;            // CseDeviceState
+constexpr size_t kSmallUnbwt = kSmallCse + 1024;              // inverse-BWT counters
+constexpr size_t kSmallBytes = 64 * 1024;
+
+// ---- stage entry points (each launches kernels on ctx->stream) --------------------
+// radix_sort.cu: LSD radix sort of (u64 key, u32 value) pairs on digit shifts[0..npass).
+// Buffers are ping-ponged; *out_k / *out_v receive the pointers that hold the result.
+int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uint32_t* valB,
+                     uint32_t m, const int* shifts, int npass, uint64_t** out_k, uint32_t** out_v,
+                     int* passes_run);
+size_t radix_desc_words(uint32_t m);
+
+// suffix_sort.cu
+int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host_or_null);
+// wavelet.cu
+int wavelet_build(Ctx* c, uint32_t n);
+// cse.cu
+int cse_begin(Ctx* c, uint32_t n);
+int cse_advance(Ctx* c, bool resident, bce_cse_batch* out);
+void cse_destroy(Ctx* c);
+// unbwt.cu
+int unbwt_run(Ctx* c, uint32_t offset, uint32_t n, uint8_t* out_host);
+
+// api.cu helpers
+int next_tag(Ctx* c);
+int h2d(Ctx* c, void* dst, const void* src, size_t bytes);
+int d2h(Ctx* c, void* dst, const void* src, size_t bytes);
+void tic(Ctx* c);
+float toc(Ctx* c);   // ms since tic on ctx->stream (synchronises the stream)
+size_t scratch_budget(Ctx* c);
+
+}  // namespace bce

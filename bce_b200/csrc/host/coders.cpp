@@ -1,0 +1,260 @@
+// coders.cpp -- see coders.hpp.  Every routine names the reference lines whose behaviour it
+// reproduces (bce.cpp:line); the arithmetic must match bit for bit.
+#include "coders.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+
+namespace bcehost {
+
+// ---- configuration table ---------------------------------------------------------------
+static ConfigTable make_default() {
+  // context bits per (stream, k), bce.cpp:713-724, written as runs: (value, count)...
+  struct Run { uint8_t v; uint8_t n; };
+  static const Run rows[kConfigRows][6] = {
+      {{0, 2}, {5, 3}, {4, 26}, {0, 1}},
+      {{0, 2}, {5, 3}, {4, 26}, {0, 1}},
+      {{0, 2}, {5, 3}, {4, 22}, {3, 4}, {0, 1}},
+      {{0, 2}, {5, 3}, {4, 17}, {3, 9}, {0, 1}},
+      {{0, 2}, {5, 2}, {4, 8}, {3, 19}, {0, 1}},
+      {{0, 2}, {5, 2}, {4, 8}, {3, 19}, {0, 1}},
+      {{0, 2}, {5, 1}, {4, 6}, {3, 22}, {0, 1}},
+      {{0, 2}, {4, 4}, {3, 19}, {2, 6}, {0, 1}},
+      {{0, 32}},
+  };
+  ConfigTable t{};
+  for (int r = 0; r < kConfigRows; ++r) {
+    int c = 0;
+    for (const Run& run : rows[r])
+      for (int i = 0; i < run.n && c < kConfigCols; ++i) t[r][c++] = run.v;
+  }
+  return t;
+}
+
+const ConfigTable& default_config() {
+  static const ConfigTable t = make_default();
+  return t;
+}
+
+bool load_config_file(const std::string& path, ConfigTable& table) {
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  const std::streamoff size = f ? std::streamoff(f.tellg()) : -1;
+  if (size != std::streamoff(kConfigRows * kConfigCols)) {          // bce.cpp:629-632
+    std::printf("Config not found or wrong size.\n");
+    return false;
+  }
+  f.seekg(0, std::ios::beg);
+  ConfigTable tmp;
+  if (!f.read(reinterpret_cast<char*>(tmp.data()), size)) {         // bce.cpp:636-639
+    std::printf("Could not read Config.\n");
+    return false;
+  }
+  table = tmp;
+  return true;
+}
+
+bool save_config_file(const std::string& path, const ConfigTable& table) {
+  std::ofstream f(path, std::ios::binary | std::ios::trunc);
+  f.write(reinterpret_cast<const char*>(table.data()), kConfigRows * kConfigCols);
+  return bool(f);
+}
+
+// ---- range coder -----------------------------------------------------------------------
+void RangeEncoder::renormalise() {                                  // shift_out, bce.cpp:655-661
+  while (((hi_ ^ lo_) >> 48) == 0) {
+    out_.push_back(uint16_t(hi_ >> 48));
+    lo_ <<= 16;
+    hi_ = (hi_ << 16) | 0xFFFFu;
+  }
+}
+void RangeEncoder::restart_if_narrow(uint64_t total) {              // bce.cpp:520-525, :541-546
+  if (hi_ - lo_ < total) {
+    for (int shift = 48; shift >= 0; shift -= 16) out_.push_back(uint16_t(lo_ >> shift));
+    lo_ = 0;
+    hi_ = ~0ull;
+  }
+}
+void RangeEncoder::put_uniform(uint32_t sym, uint32_t range) {      // bce.cpp:538-553
+  restart_if_narrow(range);
+  const uint64_t step = (hi_ - lo_) / range;
+  lo_ += step * sym;
+  hi_ = lo_ + step - 1;
+  renormalise();
+}
+void RangeEncoder::put(uint32_t cum, uint32_t freq, uint32_t total) {   // bce.cpp:520-529, :535
+  restart_if_narrow(total);
+  const uint64_t step = (hi_ - lo_) / total;
+  lo_ += step * cum;
+  hi_ = lo_ + step * freq - 1;
+  renormalise();
+}
+void RangeEncoder::finish() {                                       // bce.cpp:610-615
+  renormalise();
+  const uint32_t bits = uint32_t(__builtin_clzll(lo_ ^ hi_)) + 1;
+  out_.push_back(uint16_t((hi_ >> (64 - bits)) << (16 - bits)));
+}
+
+RangeDecoder::RangeDecoder(const uint16_t* words, size_t count) : words_(words), count_(count) {
+  // preload four words, zero padded (bce.cpp:495-501)
+  for (int i = 0; i < 4; ++i) code_ = (code_ << 16) | next();
+}
+void RangeDecoder::renormalise() {                                  // shift_in, bce.cpp:663-669
+  while (((hi_ ^ lo_) >> 48) == 0) {
+    code_ = (code_ << 16) + next();
+    lo_ <<= 16;
+    hi_ = (hi_ << 16) | 0xFFFFu;
+  }
+}
+void RangeDecoder::restart_if_narrow(uint64_t total) {              // bce.cpp:566-571, :593-598
+  if (hi_ - lo_ < total) {
+    for (int i = 0; i < 4; ++i) code_ = (code_ << 16) + next();
+    lo_ = 0;
+    hi_ = ~0ull;
+  }
+}
+uint32_t RangeDecoder::get_uniform(uint32_t range) {                // bce.cpp:592-608
+  restart_if_narrow(range);
+  const uint64_t step = (hi_ - lo_) / range;
+  const uint32_t sym = uint32_t((code_ - lo_) / step);
+  lo_ += step * sym;
+  hi_ = lo_ + step - 1;
+  renormalise();
+  return sym;
+}
+uint32_t RangeDecoder::get(const uint8_t* row, uint32_t k, uint32_t total) {   // bce.cpp:573-581
+  restart_if_narrow(total);
+  const uint64_t step = (hi_ - lo_) / total;
+  uint64_t top = lo_ - 1;                       // wraps exactly like the reference when lo_ == 0
+  uint64_t bottom = lo_;
+  uint32_t sym = 0;
+  for (;; ++sym) {
+    bottom = top + 1;
+    top += step * (uint64_t(row[sym]) + 1);
+    if (!(top < code_) || sym + 1 >= k) break;  // the bound only matters for corrupt archives
+  }
+  lo_ = bottom;
+  hi_ = top;
+  // the reference bumps the counter before shift_in (:583-587); the two do not interact
+  renormalise();
+  return sym;
+}
+
+// ---- adaptive model --------------------------------------------------------------------
+void ContextModel::configure(const std::array<uint8_t, kConfigCols>& bits) {
+  uint32_t start = 0;
+  off_.fill(0);
+  for (uint32_t k = 2; k < uint32_t(kConfigCols); ++k) {
+    off_[k] = start | (uint32_t(bits[k]) << 24);
+    start += k << (bits[k] * 2);
+  }
+  stat_.assign(start, 0);
+}
+
+StreamEncoder::StreamEncoder(int id, const ConfigTable& cfg) {
+  const auto& bits = cfg[(id < 0 || id > 7) ? 8 : id];              // bce.cpp:683-684
+  uint32_t last = 0;
+  for (uint8_t b : bits) {                                          // bce.cpp:685-691
+    rc_.put_uniform(b != last, 2);
+    if (b != last) rc_.put_uniform(b, 6);
+    last = b;
+  }
+  model_.configure(bits);
+}
+
+void StreamEncoder::count(uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2, uint32_t cs) {
+  while (k > uint32_t(kMaxAdaptive)) {                              // bce.cpp:507-510
+    rc_.put_uniform(sym & 1u, 2);
+    k = (k + (~sym & 1u)) >> 1;
+    sym >>= 1;
+  }
+  uint8_t* row = model_.row(k, c1, c2, cs);
+  uint32_t below = sym, total = k;                                  // bce.cpp:514-518
+  for (uint32_t i = 0; i < sym; ++i) below += row[i];
+  for (uint32_t i = 0; i < k; ++i) total += row[i];
+  rc_.put(below, uint32_t(row[sym]) + 1, total);
+  ContextModel::bump(row, k, sym);
+}
+
+void StreamEncoder::varint(uint32_t v) {                            // bce.cpp:364-370
+  for (; v; v >>= 1) rc_.put_uniform(v & 1u, 3);
+  rc_.put_uniform(2, 3);
+}
+
+StreamDecoder::StreamDecoder(int id, const uint16_t* words, size_t count) : rd_(words, count) {
+  (void)id;                                                          // the row travels in the stream
+  std::array<uint8_t, kConfigCols> bits{};
+  uint32_t last = 0;
+  for (auto& b : bits) {                                            // bce.cpp:693-697
+    b = uint8_t(rd_.get_uniform(2) ? rd_.get_uniform(6) : last);
+    last = b;
+  }
+  model_.configure(bits);
+}
+
+uint32_t StreamDecoder::count(uint32_t k, uint32_t c1, uint32_t c2, uint32_t cs) {   // bce.cpp:555-590
+  if (k > uint32_t(kMaxAdaptive)) {
+    const uint32_t low = rd_.get_uniform(2);
+    return (count((k + (~low & 1u)) >> 1, c1, c2, cs) << 1) | low;
+  }
+  uint8_t* row = model_.row(k, c1, c2, cs);
+  uint32_t total = k;
+  for (uint32_t i = 0; i < k; ++i) total += row[i];
+  const uint32_t sym = rd_.get(row, k, total);
+  ContextModel::bump(row, k, sym);
+  return sym;
+}
+
+uint32_t StreamDecoder::varint() {                                  // bce.cpp:372-377
+  uint32_t v = 0;
+  for (int i = 0; i < 31; ++i) {
+    const uint32_t d = rd_.get_uniform(3);
+    if (d == 2) break;
+    v |= d << i;
+  }
+  return v;
+}
+
+// ---- scan policy -----------------------------------------------------------------------
+void ScanCollector::count(uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2, uint32_t cs) {
+  while (k > uint32_t(kMaxAdaptive)) {                              // bce.cpp:738-741 (note: not :509's halving)
+    nats_ += std::log(2);
+    k = (k >> 1) + (~sym & 1u);
+    sym >>= 1;
+  }
+  stat_[k][(((c2 << 8) / cs) << 16) | ((c1 << 8) / cs)].push_back(uint8_t(sym));   // bce.cpp:743
+}
+
+void ScanCollector::finish(ConfigTable& table) {                    // bce.cpp:751-800
+  std::vector<uint16_t> sim;
+  for (uint32_t k = 2; k < uint32_t(kMaxAdaptive); ++k) {
+    double best = 0;
+    for (auto& kv : stat_[k]) best += std::log(k) * kv.second.size();
+    for (uint32_t bits = 0; bits <= 5; ++bits) {
+      sim.assign(size_t(k) << (2 * bits), 0);
+      double z = 0;
+      for (auto& kv : stat_[k]) {
+        uint32_t key = kv.first;
+        uint16_t q1 = uint16_t(key), q2 = uint16_t(key >> 16);
+        q1 >>= 8 - bits;
+        q2 >>= 8 - bits;
+        uint16_t* ctx = &sim[size_t((uint32_t(q1) << bits) | q2) * k];
+        for (uint8_t s : kv.second) {
+          uint32_t total = k;
+          for (uint32_t i = 0; i < k; ++i) total += ctx[i];
+          z += std::log(static_cast<double>(total) / (1 + ctx[s]));
+          if (++ctx[s] == 0xFF)
+            for (uint32_t i = 0; i < k; ++i) ctx[i] >>= 1;
+        }
+      }
+      if (z < best) {
+        best = z;
+        table[row_][k] = uint8_t(bits);
+      }
+    }
+    nats_ += best;
+  }
+  std::printf("Result size: %.1f B\n", nats_ / std::log(256));
+}
+
+}  // namespace bcehost

@@ -1,0 +1,112 @@
+// host_api.cpp -- extern "C" surface of libbce_host (include/bce_host.h).
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../../include/bce_host.h"
+#include "archive.hpp"
+
+using namespace bcehost;
+
+struct bce_archive_writer { ArchiveWriter* w; };
+struct bce_scan { ScanSession* s; };
+
+static ConfigTable table_from(const uint8_t* cfg288) {
+  ConfigTable t = default_config();
+  if (cfg288) std::memcpy(t.data(), cfg288, 288);
+  return t;
+}
+
+extern "C" {
+
+const uint8_t* bce_host_default_config(void) {
+  return reinterpret_cast<const uint8_t*>(default_config().data());
+}
+void bce_host_free(void* p) { std::free(p); }
+
+bce_archive_writer* bce_archive_begin(uint32_t n, const uint32_t C[8], const uint8_t* cfg288) {
+  if (!C || n == 0) return nullptr;
+  auto* h = new (std::nothrow) bce_archive_writer{nullptr};
+  if (!h) return nullptr;
+  h->w = new (std::nothrow) ArchiveWriter(n, C, table_from(cfg288));
+  if (!h->w) { delete h; return nullptr; }
+  return h;
+}
+int bce_archive_feed(bce_archive_writer* h, const bce_cse_batch* batch, int threads) {
+  if (!h || !batch) return BCE_GPU_E_ARG;
+  h->w->feed(*batch, threads);
+  return BCE_GPU_OK;
+}
+int bce_archive_finish(bce_archive_writer* h, uint32_t offset, uint16_t** words, size_t* nwords) {
+  if (!h || !words || !nwords) return BCE_GPU_E_ARG;
+  std::vector<uint16_t> out = h->w->finish(offset);
+  delete h->w;
+  delete h;
+  uint16_t* mem = static_cast<uint16_t*>(std::malloc(out.size() * sizeof(uint16_t) + 2));
+  if (!mem) return BCE_GPU_E_NOMEM;
+  std::memcpy(mem, out.data(), out.size() * sizeof(uint16_t));
+  *words = mem;
+  *nwords = out.size();
+  return BCE_GPU_OK;
+}
+void bce_archive_abort(bce_archive_writer* h) {
+  if (!h) return;
+  delete h->w;
+  delete h;
+}
+
+bce_scan* bce_scan_begin(void) {
+  auto* h = new (std::nothrow) bce_scan{nullptr};
+  if (!h) return nullptr;
+  h->s = new (std::nothrow) ScanSession();
+  if (!h->s) { delete h; return nullptr; }
+  return h;
+}
+int bce_scan_feed(bce_scan* h, const bce_cse_batch* batch) {
+  if (!h || !batch) return BCE_GPU_E_ARG;
+  h->s->feed(*batch);
+  return BCE_GPU_OK;
+}
+int bce_scan_finish(bce_scan* h, uint8_t cfg288_out[288]) {
+  if (!h || !cfg288_out) return BCE_GPU_E_ARG;
+  ConfigTable t = h->s->finish();
+  std::memcpy(cfg288_out, t.data(), 288);
+  delete h->s;
+  delete h;
+  return BCE_GPU_OK;
+}
+
+#ifndef BCE_HOST_NO_GPU
+int bce_compress_buffer(bce_gpu_ctx* ctx, const uint8_t* T, uint32_t n, const uint8_t* cfg288, int threads,
+                        uint16_t** words, size_t* nwords) {
+  uint32_t offset = 0, C[8];
+  int rc = bce_gpu_compress_front(ctx, T, n, &offset, C);           // RankFile ctor, bce.cpp:1411
+  if (rc) return rc;
+  bce_archive_writer* w = bce_archive_begin(n, C, cfg288);          // BCE::encode, bce.cpp:1417
+  if (!w) return BCE_GPU_E_NOMEM;
+  bce_cse_batch batch;
+  do {
+    rc = bce_gpu_cse_next(ctx, &batch);
+    if (rc) { bce_archive_abort(w); return rc; }
+    bce_archive_feed(w, &batch, threads);
+  } while (!batch.done);
+  return bce_archive_finish(w, offset, words, nwords);
+}
+
+int bce_scan_buffer(bce_gpu_ctx* ctx, const uint8_t* T, uint32_t n, uint8_t cfg288_out[288]) {
+  uint32_t offset = 0, C[8];
+  int rc = bce_gpu_compress_front(ctx, T, n, &offset, C);
+  if (rc) return rc;
+  bce_scan* s = bce_scan_begin();
+  if (!s) return BCE_GPU_E_NOMEM;
+  bce_cse_batch batch;
+  do {
+    rc = bce_gpu_cse_next(ctx, &batch);
+    if (rc) { delete s->s; delete s; return rc; }
+    bce_scan_feed(s, &batch);
+  } while (!batch.done);
+  return bce_scan_finish(s, cfg288_out);
+}
+#endif
+
+}  // extern "C"

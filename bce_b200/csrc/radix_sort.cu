@@ -1,0 +1,215 @@
+// radix_sort.cu -- LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits.
+//
+// This is the sort core that replaces libdivsufsort's suffix sorter (call site
+// bce.cpp:901) in the prefix-doubling suffix sort (suffix_sort.cu).  One pass is a
+// single kernel ("onesweep"): every tile ranks its elements by digit in shared memory,
+// learns where its digit runs start in the output through a chained scan over tiles
+// (decoupled look-back on tagged descriptors, common.cuh), and writes keys and values
+// out of a shared-memory staging buffer so that every digit run is a coalesced burst.
+// Digit histograms for all passes of one sort come from one extra read of the keys.
+//
+// HBM traffic per pass: read 12 B + write 12 B per element  (24 m P_r).
+#include "ctx.h"
+
+namespace bce {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 12;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_MAX_PASSES = 8;
+
+struct RadixShifts { int s[RS_MAX_PASSES]; };
+
+size_t radix_desc_words(uint32_t m) { return (size_t(m) / RS_TILE + 1) * 256; }
+
+// ---- histograms of every digit position in one read ------------------------------
+__global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t* __restrict__ keys, uint32_t m,
+                                                         int npass, RadixShifts sh,
+                                                         uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[RS_MAX_PASSES][256];
+  for (int i = threadIdx.x; i < RS_MAX_PASSES * 256; i += blockDim.x) (&h[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    uint64_t k = keys[i];
+    for (int p = 0; p < npass; ++p) atomicAdd(&h[p][(k >> sh.s[p]) & 255u], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < npass * 256; i += blockDim.x) {
+    uint32_t v = (&h[0][0])[i];
+    if (v) atomicAdd(&hist[i], v);
+  }
+}
+
+// ---- one pass ------------------------------------------------------------------------
+struct RadixPass {
+  const uint64_t* kin;
+  const uint32_t* vin;
+  uint64_t* kout;
+  uint32_t* vout;
+  uint32_t m;
+  int shift;
+  const uint32_t* base;   // [256] exclusive start of every digit in the output
+  uint64_t* desc;         // [tiles][256] tagged descriptors
+  uint32_t* ticket;       // tile dispenser (zero at launch)
+  uint32_t tag;
+  uint32_t* err;
+};
+
+__global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(RadixPass p) {
+  __shared__ uint64_t s_keys[RS_TILE];
+  __shared__ uint32_t s_vals[RS_TILE];
+  __shared__ uint32_t s_whist[RS_WARPS][256];
+  __shared__ uint32_t s_goff[256];
+  __shared__ uint32_t s_dstart[256];
+  __shared__ uint32_t s_scan[RS_WARPS];
+  __shared__ uint32_t s_tile;
+
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // tiles are handed out in launch order so that every predecessor is already running
+  if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
+  for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s_whist[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t tile_base = tile * uint32_t(RS_TILE);
+  const uint32_t valid = min(uint32_t(RS_TILE), p.m - tile_base);
+  const uint32_t wbase = tile_base + warp * (32 * RS_ITEMS);
+
+  uint64_t key[RS_ITEMS];
+  uint32_t val[RS_ITEMS];
+  uint32_t pos[RS_ITEMS];
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    uint32_t idx = wbase + k * 32 + lane;
+    bool in = idx < p.m;
+    key[k] = in ? p.kin[idx] : ~0ull;      // padding sorts to the very end of the tile
+    val[k] = in ? p.vin[idx] : 0u;
+  }
+  // rank inside the warp's chunk, in index order (stable)
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    uint32_t d = uint32_t(key[k] >> p.shift) & 255u;
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    unsigned leader = __ffs(peers) - 1;
+    uint32_t before = 0;
+    if (lane == leader) {
+      before = s_whist[warp][d];
+      s_whist[warp][d] = before + __popc(peers);
+    }
+    before = __shfl_sync(0xffffffffu, before, leader);
+    pos[k] = before + __popc(peers & lanemask_lt());
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // thread d owns digit d: turn per-warp counts into per-warp offsets, get the tile count
+  {
+    const uint32_t d = tid;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      uint32_t c = s_whist[w][d];
+      s_whist[w][d] = sum;
+      sum += c;
+    }
+    uint32_t tot;
+    uint32_t dstart = block_exclusive_scan<uint32_t, RS_THREADS>(sum, s_scan, tot);
+    s_dstart[d] = dstart;
+    uint32_t publish = (d == 255u) ? sum - (uint32_t(RS_TILE) - valid) : sum;
+    uint32_t excl = lookback_serial(p.desc + d, 256u, tile, p.tag, publish, p.err);
+    s_goff[d] = p.base[d] + excl - dstart;     // global index = s_goff[digit] + local index
+  }
+  __syncthreads();
+
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    uint32_t d = uint32_t(key[k] >> p.shift) & 255u;
+    pos[k] += s_dstart[d] + s_whist[warp][d];
+    s_keys[pos[k]] = key[k];
+    s_vals[pos[k]] = val[k];
+  }
+  __syncthreads();
+  for (uint32_t j = tid; j < valid; j += RS_THREADS) {
+    uint64_t k64 = s_keys[j];
+    uint32_t d = uint32_t(k64 >> p.shift) & 255u;
+    uint32_t g = s_goff[d] + j;
+    p.kout[g] = k64;
+    p.vout[g] = s_vals[j];
+  }
+}
+
+int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uint32_t* valB,
+                     uint32_t m, const int* shifts, int npass, uint64_t** out_k, uint32_t** out_v,
+                     int* passes_run) {
+  *out_k = keyA;
+  *out_v = valA;
+  if (passes_run) *passes_run = 0;
+  if (m <= 1 || npass <= 0) return BCE_GPU_OK;
+  if (npass > RS_MAX_PASSES) return BCE_GPU_E_ARG;
+
+  char* small = c->small.as<char>();
+  uint32_t* d_hist = reinterpret_cast<uint32_t*>(small + kSmallHist);
+  uint32_t* d_base = reinterpret_cast<uint32_t*>(small + kSmallBase);
+  uint32_t* d_ticket = reinterpret_cast<uint32_t*>(small + kSmallTicket);
+  uint32_t* d_err = reinterpret_cast<uint32_t*>(small + kSmallErr);
+  uint32_t* h_hist = c->pinned_small.as<uint32_t>();
+
+  BCE_TRY(c->desc.ensure(c, radix_desc_words(m) * sizeof(uint64_t)));
+
+  RadixShifts sh;
+  for (int i = 0; i < RS_MAX_PASSES; ++i) sh.s[i] = i < npass ? shifts[i] : 0;
+  BCE_CUDA(c, cudaMemsetAsync(d_hist, 0, kSmallErr, c->stream));   // hist, base, tickets (err is the caller's)
+  uint64_t hb64 = (uint64_t(m) + 255) / 256, hbmax = uint64_t(c->sm_count) * 8;
+  int hb = int(hb64 < hbmax ? hb64 : hbmax);
+  radix_hist_kernel<<<hb, 256, 0, c->stream>>>(keyA, m, npass, sh, d_hist);
+  c->stats.gpu_launches++;
+  BCE_CUDA(c, cudaGetLastError());
+  BCE_CUDA(c, cudaMemcpyAsync(h_hist, d_hist, npass * 256 * 4, cudaMemcpyDeviceToHost, c->stream));
+  BCE_CUDA(c, cudaStreamSynchronize(c->stream));
+
+  // exclusive scans on the host (8 x 256 values); passes whose digit is constant are skipped
+  bool run[RS_MAX_PASSES];
+  uint32_t* h_base = h_hist + RS_MAX_PASSES * 256;
+  for (int p = 0; p < npass; ++p) {
+    run[p] = true;
+    uint32_t acc = 0;
+    for (int d = 0; d < 256; ++d) {
+      uint32_t cnt = h_hist[p * 256 + d];
+      if (cnt == m) run[p] = false;
+      h_base[p * 256 + d] = acc;
+      acc += cnt;
+    }
+  }
+  BCE_CUDA(c, cudaMemcpyAsync(d_base, h_base, npass * 256 * 4, cudaMemcpyHostToDevice, c->stream));
+
+  uint64_t* kin = keyA; uint64_t* kout = keyB;
+  uint32_t* vin = valA; uint32_t* vout = valB;
+  const uint32_t tiles = (m + RS_TILE - 1) / RS_TILE;
+  int ran = 0;
+  for (int p = 0; p < npass; ++p) {
+    if (!run[p]) continue;
+    RadixPass a;
+    a.kin = kin; a.vin = vin; a.kout = kout; a.vout = vout;
+    a.m = m; a.shift = shifts[p];
+    a.base = d_base + p * 256;
+    a.desc = c->desc.as<uint64_t>();
+    a.ticket = d_ticket + p;
+    a.tag = uint32_t(next_tag(c));
+    a.err = d_err;
+    radix_onesweep_kernel<<<tiles, RS_THREADS, 0, c->stream>>>(a);
+    c->stats.gpu_launches++;
+    c->stats.radix_launches++;
+    c->stats.radix_elems += m;
+    BCE_CUDA(c, cudaGetLastError());
+    uint64_t* tk = kin; kin = kout; kout = tk;
+    uint32_t* tv = vin; vin = vout; vout = tv;
+    ++ran;
+  }
+  *out_k = kin;
+  *out_v = vin;
+  if (passes_run) *passes_run = ran;
+  return BCE_GPU_OK;
+}
+
+}  // namespace bce

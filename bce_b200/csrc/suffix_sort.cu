@@ -1,0 +1,389 @@
+// suffix_sort.cu -- stage A: cyclic suffix sort and BWT on the device.
+//
+// Replaces File::rotate (bce.cpp:858-894) and File::bwt / divbwt (bce.cpp:896-910).
+// The reference rotates the text to its least rotation and suffix-sorts it with
+// libdivsufsort; the net effect is the BWT of the *cyclic rotations*
+// of T with row 0 = least rotation and offset = its start index.  Here all n rotations
+// are sorted directly by prefix doubling over packed rank keys:
+//
+//   round 0   key(i) = 8 bytes T[i..i+8) (cyclic, big-endian); LSD radix sort of (key, i)
+//   re-rank   rank[i] = SA position of the head of i's group; rotations alone in their
+//             group are final and leave the working set
+//   round r   key = (dense group id << 32) | rank[(i + h) mod n], h = 8 * 2^(r-1);
+//             radix sort of the working set; groups stay where they are, so the list slot
+//             of an element fixes its SA position
+//   end       working set empty, or h >= n (T is a power w^k: remaining ties are identical
+//             rotations, ordered by index so that offset is the smallest one)
+//
+// Kernels: K1 pack, K2 radix pass (radix_sort.cu), K3 re-rank + stable compaction
+// (single pass, chained scan), K4 key rebuild (gather-bound), K5 BWT gather (gather-bound).
+#include "ctx.h"
+
+namespace bce {
+
+// ---------------------------------------------------------------------------------
+// K0: make T cyclic for 64 bytes past the end so that window reads need no modulo
+// ---------------------------------------------------------------------------------
+__global__ void pad_cyclic_kernel(uint8_t* T, uint32_t n) {
+  uint32_t k = threadIdx.x;
+  if (k < 64) T[size_t(n) + k] = T[k % n];
+}
+
+// ---------------------------------------------------------------------------------
+// K1: pack 8-byte big-endian keys; one thread makes the 8 keys of an aligned octet
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t bswap64(uint64_t v) {
+  uint32_t lo = uint32_t(v), hi = uint32_t(v >> 32);
+  return (uint64_t(__byte_perm(lo, 0, 0x0123)) << 32) | __byte_perm(hi, 0, 0x0123);
+}
+
+__global__ void __launch_bounds__(256) pack_keys_kernel(const uint8_t* __restrict__ T, uint32_t n,
+                                                        uint64_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ idx) {
+  const uint32_t octets = (n + 7) / 8;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= octets) return;
+  const uint64_t* T64 = reinterpret_cast<const uint64_t*>(T);
+  uint64_t b0 = bswap64(T64[t]), b1 = bswap64(T64[t + 1]);
+  uint64_t k[8];
+  k[0] = b0;
+#pragma unroll
+  for (int j = 1; j < 8; ++j) k[j] = (b0 << (8 * j)) | (b1 >> (64 - 8 * j));
+  const uint32_t i0 = t * 8;
+  if (i0 + 8 <= n) {
+    ulonglong2* ko = reinterpret_cast<ulonglong2*>(keys + i0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ko[j] = make_ulonglong2(k[2 * j], k[2 * j + 1]);
+    uint4* io = reinterpret_cast<uint4*>(idx + i0);
+    io[0] = make_uint4(i0, i0 + 1, i0 + 2, i0 + 3);
+    io[1] = make_uint4(i0 + 4, i0 + 5, i0 + 6, i0 + 7);
+  } else {
+    for (int j = 0; j < 8 && i0 + j < n; ++j) { keys[i0 + j] = k[j]; idx[i0 + j] = i0 + j; }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K3: re-rank + stable compaction of the rotations that are still tied
+// ---------------------------------------------------------------------------------
+constexpr int RR_THREADS = 256;
+constexpr int RR_ITEMS = 4;
+constexpr int RR_TILE = RR_THREADS * RR_ITEMS;
+
+struct RerankArgs {
+  const uint64_t* key;      // sorted keys of the working set
+  const uint32_t* idx;      // rotation start of every slot (sorted along with the keys)
+  const uint32_t* sapos;    // SA position of every slot (NULL in round 0: slot == SA position)
+  uint32_t m;
+  uint32_t* sa;
+  uint32_t* rnk;
+  uint32_t* idx_out;        // compacted working set of the next round
+  uint32_t* sapos_out;
+  uint32_t* gd_out;         // dense group id of every survivor
+  uint32_t* totals;         // [0] survivors, [1] surviving groups
+  uint64_t* desc;           // 3 x tiles tagged descriptors
+  uint32_t tiles;
+  uint32_t* ticket;
+  uint32_t tag;
+  uint32_t* err;
+};
+
+__global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
+  __shared__ uint32_t s_scan32[RR_THREADS / 32];
+  __shared__ uint64_t s_scan64[RR_THREADS / 32];
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_carry[3];
+
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  const uint32_t q0 = tile * RR_TILE + tid * RR_ITEMS;
+
+  uint64_t key[RR_ITEMS + 2];     // key[0] = predecessor, key[ITEMS+1] = successor
+  uint32_t idx[RR_ITEMS], sap[RR_ITEMS];
+#pragma unroll
+  for (int j = 0; j < RR_ITEMS; ++j) {
+    uint32_t q = q0 + j;
+    bool in = q < a.m;
+    key[j + 1] = in ? a.key[q] : 0;
+    idx[j] = in ? a.idx[q] : 0;
+    sap[j] = in ? (a.sapos ? a.sapos[q] : q) : 0;
+  }
+  key[0] = (q0 > 0 && q0 - 1 < a.m) ? a.key[q0 - 1] : 0;
+  key[RR_ITEMS + 1] = (q0 + RR_ITEMS < a.m) ? a.key[q0 + RR_ITEMS] : 0;
+
+  // head = first slot of a (new) group; lone = group of one
+  uint32_t head_bits = 0, surv_bits = 0, shead_bits = 0;
+  uint32_t last_head = 0;            // (slot + 1) of the most recent head in this thread
+  uint32_t nsurv = 0, nshead = 0;
+#pragma unroll
+  for (int j = 0; j < RR_ITEMS; ++j) {
+    uint32_t q = q0 + j;
+    if (q < a.m) {
+      bool head = (q == 0) || key[j + 1] != key[j];
+      bool next_head = (q + 1 == a.m) || key[j + 2] != key[j + 1];
+      bool lone = head && next_head;
+      if (head) { head_bits |= 1u << j; last_head = q + 1; }
+      if (!lone) { surv_bits |= 1u << j; ++nsurv; }
+      if (head && !lone) { shead_bits |= 1u << j; ++nshead; }
+    }
+  }
+
+  // (1) block-wide inclusive max-scan of last_head  ->  head slot for every element
+  uint32_t inc = last_head;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= unsigned(d)) inc = max(inc, o);
+  }
+  if (lane == 31) s_scan32[warp] = inc;
+  // (2) block-wide exclusive sum-scan of (survivors, surviving heads) packed in 64 bits
+  uint64_t packed = uint64_t(nsurv) | (uint64_t(nshead) << 32);
+  uint64_t inc64 = packed;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t o = __shfl_up_sync(0xffffffffu, inc64, d);
+    if (lane >= unsigned(d)) inc64 += o;
+  }
+  if (lane == 31) s_scan64[warp] = inc64;
+  __syncthreads();
+  uint32_t carry_head = 0, tile_head = 0;
+  uint64_t woff = 0, tile_sum = 0;
+#pragma unroll
+  for (int w = 0; w < RR_THREADS / 32; ++w) {
+    uint32_t hv = s_scan32[w];
+    uint64_t sv = s_scan64[w];
+    if (unsigned(w) < warp) { carry_head = max(carry_head, hv); woff += sv; }
+    tile_head = max(tile_head, hv);
+    tile_sum += sv;
+  }
+  // exclusive (over threads) last head before this thread's first slot
+  uint32_t prev_inc = __shfl_up_sync(0xffffffffu, inc, 1);
+  uint32_t head_before = max(carry_head, lane ? prev_inc : 0u);
+  uint64_t excl64 = woff + inc64 - packed;
+
+  // (3) carries across tiles: three independent chained scans
+  if (tid < 3) {
+    uint64_t* d = a.desc + size_t(tid) * a.tiles;
+    uint32_t v;
+    if (tid == 0) v = lookback_serial_last(d, 1u, tile, a.tag, tile_head, a.err);
+    else if (tid == 1) v = lookback_serial(d, 1u, tile, a.tag, uint32_t(tile_sum), a.err);
+    else v = lookback_serial(d, 1u, tile, a.tag, uint32_t(tile_sum >> 32), a.err);
+    s_carry[tid] = v;
+  }
+  __syncthreads();
+  const uint32_t tile_head_carry = s_carry[0];
+  uint32_t out_at = s_carry[1] + uint32_t(excl64);
+  uint32_t gd_run = s_carry[2] + uint32_t(excl64 >> 32);    // surviving heads before this thread
+
+  uint32_t cur_head = max(head_before, tile_head_carry);      // (slot+1) of the governing head
+#pragma unroll
+  for (int j = 0; j < RR_ITEMS; ++j) {
+    uint32_t q = q0 + j;
+    if (q >= a.m) break;
+    if (head_bits >> j & 1u) cur_head = q + 1;
+    if (shead_bits >> j & 1u) ++gd_run;
+    // slots of one group are consecutive in SA, so the head's SA position is sap - distance
+    uint32_t rank = sap[j] - (q - (cur_head - 1));
+    a.sa[sap[j]] = idx[j];
+    a.rnk[idx[j]] = rank;
+    if (surv_bits >> j & 1u) {
+      a.idx_out[out_at] = idx[j];
+      a.sapos_out[out_at] = sap[j];
+      a.gd_out[out_at] = gd_run - 1;
+      ++out_at;
+    }
+  }
+  if (tile == a.tiles - 1 && tid == RR_THREADS - 1) {
+    a.totals[0] = s_carry[1] + uint32_t(tile_sum);
+    a.totals[1] = s_carry[2] + uint32_t(tile_sum >> 32);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// K4: key rebuild for the next doubling step (gather-bound)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rekey_kernel(const uint32_t* __restrict__ idx,
+                                                    const uint32_t* __restrict__ gd,
+                                                    const uint32_t* __restrict__ rnk, uint32_t m,
+                                                    uint32_t n, uint32_t h, int tiebreak,
+                                                    uint64_t* __restrict__ key) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  uint32_t i = idx[q];
+  uint32_t second;
+  if (tiebreak) {
+    second = i;                       // identical rotations: order by start index
+  } else {
+    uint64_t j = uint64_t(i) + h;
+    if (j >= n) j -= n;
+    second = rnk[j];
+  }
+  key[q] = (uint64_t(gd[q]) << 32) | second;
+}
+
+// ---------------------------------------------------------------------------------
+// K5: BWT gather  L[r] = T[(SA[r] - 1) mod n]   (bce.cpp:901-902 net effect)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bwt_gather_kernel(const uint8_t* __restrict__ T,
+                                                         const uint32_t* __restrict__ sa, uint32_t n,
+                                                         uint8_t* __restrict__ L) {
+  uint32_t r4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (r4 >= n) return;
+  uint32_t out = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t r = r4 + j;
+    if (r < n) {
+      uint32_t s = sa[r];
+      uint32_t c = T[s ? s - 1 : n - 1];
+      out |= c << (8 * j);
+    }
+  }
+  if (r4 + 4 <= n) *reinterpret_cast<uint32_t*>(L + r4) = out;
+  else for (int j = 0; r4 + j < n; ++j) L[r4 + j] = uint8_t(out >> (8 * j));
+}
+
+static inline int bits_for(uint32_t values) {   // bits needed for 0 .. values-1
+  int b = 0;
+  while (b < 32 && (uint64_t(1) << b) < values) ++b;
+  return b ? b : 1;
+}
+
+int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
+  cudaStream_t st = c->stream;
+  uint8_t* T = c->text.as<uint8_t>();
+  BCE_TRY(c->bwt.ensure(c, size_t(n) + 64));
+  uint8_t* L = c->bwt.as<uint8_t>();
+
+  // scratch: two key buffers, two index buffers, SA, rank, and the positional side arrays
+  const size_t N = n;
+  size_t need = 2 * Carver::need(N, 8) + 8 * Carver::need(N, 4) + 4096;
+  BCE_TRY(c->scratch.ensure(c, need));
+  Carver cv(c->scratch.p, c->scratch.cap);
+  uint64_t* keyA = cv.take<uint64_t>(N);
+  uint64_t* keyB = cv.take<uint64_t>(N);
+  uint32_t* idxA = cv.take<uint32_t>(N);
+  uint32_t* idxB = cv.take<uint32_t>(N);
+  uint32_t* sa = cv.take<uint32_t>(N);
+  uint32_t* rnk = cv.take<uint32_t>(N);
+  uint32_t* saposA = cv.take<uint32_t>(N);
+  uint32_t* saposB = cv.take<uint32_t>(N);
+  uint32_t* gdA = cv.take<uint32_t>(N);
+  uint32_t* gdB = cv.take<uint32_t>(N);
+  if (!cv.ok()) { set_error(c, "suffix sort: scratch carve failed"); return BCE_GPU_E_NOMEM; }
+
+  char* small = c->small.as<char>();
+  uint32_t* d_err = reinterpret_cast<uint32_t*>(small + kSmallErr);
+  uint32_t* d_ticket = reinterpret_cast<uint32_t*>(small + kSmallRerankTicket);
+  uint32_t* d_totals = reinterpret_cast<uint32_t*>(small + kSmallRerankTotals);
+  uint32_t* h_small = c->pinned_small.as<uint32_t>() + 8192;   // past the sort's host mirror
+  BCE_CUDA(c, cudaMemsetAsync(d_err, 0, 64, st));
+
+  bce_gpu_stats& S = c->stats;
+  S.sort_rounds = 0;
+
+  cudaEvent_t e0 = c->ev[0], e1 = c->ev[1];
+  auto lap = [&](float& acc) -> int {
+    BCE_CUDA(c, cudaEventRecord(e1, st));
+    BCE_CUDA(c, cudaEventSynchronize(e1));
+    float ms = 0;
+    BCE_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+    acc += ms;
+    BCE_CUDA(c, cudaEventRecord(e0, st));
+    return BCE_GPU_OK;
+  };
+  BCE_CUDA(c, cudaEventRecord(e0, st));
+
+  pad_cyclic_kernel<<<1, 64, 0, st>>>(T, n);
+  {
+    uint32_t octets = (n + 7) / 8;
+    pack_keys_kernel<<<(octets + 255) / 256, 256, 0, st>>>(T, n, keyA, idxA);
+    S.gpu_launches += 2;
+  }
+  BCE_CUDA(c, cudaGetLastError());
+  BCE_TRY(lap(S.ms_pack));
+
+  uint64_t* kcur = keyA; uint64_t* kalt = keyB;
+  uint32_t* vcur = idxA; uint32_t* valt = idxB;
+  uint32_t* sap_cur = nullptr;            // round 0: slot == SA position
+  uint32_t* sap_next = saposA;
+  uint32_t* gd_next = gdA;
+  uint32_t m = n, groups = 0;
+  uint64_t h = 8;
+  const int nbits = bits_for(n);
+
+  for (int round = 0;; ++round) {
+    if (round >= kMaxSortRounds) { set_error(c, "suffix sort: too many rounds"); return BCE_GPU_E_INTERNAL; }
+    int shifts[8], np = 0;
+    bool tiebreak = false;
+    if (round == 0) {
+      for (int s = 0; s < 64; s += 8) shifts[np++] = s;
+    } else {
+      tiebreak = h >= n;
+      for (int s = 0; s < nbits; s += 8) shifts[np++] = s;
+      int gbits = bits_for(groups);
+      for (int s = 0; s < gbits && np < 8; s += 8) shifts[np++] = 32 + s;
+      // working-set slot -> key of the next doubling step
+      rekey_kernel<<<(m + 255) / 256, 256, 0, st>>>(vcur, gd_next == gdA ? gdB : gdA, rnk, m, n,
+                                                    uint32_t(tiebreak ? 0 : h), tiebreak ? 1 : 0, kcur);
+      S.gpu_launches++;
+      BCE_CUDA(c, cudaGetLastError());
+      BCE_TRY(lap(S.ms_rekey));
+    }
+    uint64_t* ks; uint32_t* vs; int ran = 0;
+    BCE_TRY(radix_sort_pairs(c, kcur, kalt, vcur, valt, m, shifts, np, &ks, &vs, &ran));
+    BCE_TRY(lap(S.ms_radix));
+    S.sort_m[round] = m;
+    S.sort_passes[round] = uint32_t(ran);
+    S.sort_rounds = uint32_t(round + 1);
+
+    // re-rank: writes SA and rank for every slot, compacts the still-tied slots
+    uint32_t* v_other = (vs == idxA) ? idxB : idxA;
+    RerankArgs a;
+    a.key = ks; a.idx = vs; a.sapos = sap_cur; a.m = m;
+    a.sa = sa; a.rnk = rnk;
+    a.idx_out = v_other; a.sapos_out = sap_next; a.gd_out = gd_next;
+    a.totals = d_totals;
+    a.tiles = (m + RR_TILE - 1) / RR_TILE;
+    BCE_TRY(c->desc.ensure(c, size_t(a.tiles) * 3 * sizeof(uint64_t)));
+    a.desc = c->desc.as<uint64_t>();
+    a.ticket = d_ticket;
+    a.tag = uint32_t(next_tag(c));
+    a.err = d_err;
+    BCE_CUDA(c, cudaMemsetAsync(d_ticket, 0, 4, st));
+    rerank_kernel<<<a.tiles, RR_THREADS, 0, st>>>(a);
+    S.gpu_launches++;
+    BCE_CUDA(c, cudaGetLastError());
+    BCE_CUDA(c, cudaMemcpyAsync(h_small, d_totals, 8, cudaMemcpyDeviceToHost, st));
+    BCE_CUDA(c, cudaMemcpyAsync(h_small + 2, d_err, 4, cudaMemcpyDeviceToHost, st));
+    BCE_TRY(lap(S.ms_rerank));      // synchronises
+    if (h_small[2]) { set_error(c, "suffix sort: chained-scan watchdog fired"); return BCE_GPU_E_INTERNAL; }
+    uint32_t m_next = h_small[0];
+    groups = h_small[1];
+    if (tiebreak && m_next) { set_error(c, "suffix sort: ties left after index tie-break"); return BCE_GPU_E_INTERNAL; }
+
+    // next round: survivors live in v_other / sap_next / gd_next
+    vcur = v_other; valt = (v_other == idxA) ? idxB : idxA;
+    kcur = keyA; kalt = keyB;
+    sap_cur = sap_next;
+    sap_next = (sap_next == saposA) ? saposB : saposA;
+    gd_next = (gd_next == gdA) ? gdB : gdA;
+    m = m_next;
+    if (m == 0) break;
+    if (round > 0) h *= 2;
+    if (round == 0) h = 8;
+  }
+
+  bwt_gather_kernel<<<((n + 3) / 4 + 255) / 256, 256, 0, st>>>(T, sa, n, L);
+  S.gpu_launches++;
+  BCE_CUDA(c, cudaGetLastError());
+  BCE_CUDA(c, cudaMemcpyAsync(h_small, sa, 4, cudaMemcpyDeviceToHost, st));
+  BCE_TRY(lap(S.ms_bwt_gather));
+  c->offset = h_small[0];
+  c->bwt_resident = true;
+  if (sa_host) BCE_TRY(d2h(c, sa_host, sa, N * 4));
+  return BCE_GPU_OK;
+}
+
+}  // namespace bce

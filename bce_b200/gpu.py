@@ -1,0 +1,247 @@
+"""ctypes binding of the C ABI in include/bce_gpu.h (libbce_gpu.so).
+
+This is plumbing for tests, bench.py and the batch driver; the product boundary is the
+C ABI itself (the `bce` tool in csrc/host links it directly).  There is no CPU fallback:
+if the CUDA library is missing or no sm_100 device is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+_LIB_PATH = _PKG / "libbce_gpu.so"
+
+ERRORS = {
+    0: "ok", -1: "bad argument", -2: "out of memory", -3: "CUDA failure",
+    -4: "call sequence violated", -5: "CSE frontier exceeded its device memory",
+    -6: "internal consistency check failed", -7: "no usable CUDA device",
+}
+
+# every symbol include/bce_gpu.h declares (tests check that the library exports them all)
+ABI_SYMBOLS = [
+    "bce_gpu_open", "bce_gpu_close", "bce_gpu_abi_version", "bce_gpu_error_string",
+    "bce_gpu_last_error", "bce_gpu_get_stats", "bce_gpu_set_scratch_limit", "bce_gpu_bwt",
+    "bce_gpu_wavelet", "bce_gpu_cse_begin", "bce_gpu_cse_next", "bce_gpu_compress_front",
+    "bce_gpu_stage_input", "bce_gpu_front_resident", "bce_gpu_unbwt",
+]
+
+
+class BceGpuError(RuntimeError):
+    def __init__(self, code: int, detail: str = ""):
+        self.code = code
+        super().__init__(f"bce_gpu error {code} ({ERRORS.get(code, '?')}): {detail}")
+
+
+class Tuple5(C.Structure):
+    _fields_ = [("sym", C.c_uint32), ("k", C.c_uint32), ("c1", C.c_uint32), ("c2", C.c_uint32), ("cs", C.c_uint32)]
+
+
+class CseBatch(C.Structure):
+    _fields_ = [("tuples", C.POINTER(Tuple5) * 8), ("count", C.c_size_t * 8), ("done", C.c_int)]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint32), ("sort_rounds", C.c_uint32),
+        ("sort_m", C.c_uint64 * 48), ("sort_passes", C.c_uint32 * 48),
+        ("radix_launches", C.c_uint64), ("radix_elems", C.c_uint64),
+        ("cse_visits", C.c_uint64), ("cse_tuples", C.c_uint64), ("cse_rounds", C.c_uint64),
+        ("cse_launches", C.c_uint64), ("cse_peak_frontier", C.c_uint64), ("gpu_launches", C.c_uint64),
+        ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
+        ("ms_pack", C.c_float), ("ms_radix", C.c_float), ("ms_rerank", C.c_float),
+        ("ms_rekey", C.c_float), ("ms_bwt_gather", C.c_float),
+        ("ms_wavelet", C.c_float), ("ms_cse", C.c_float),
+        ("ms_unbwt_bytes", C.c_float), ("ms_unbwt_chase", C.c_float),
+        ("ms_bwt_total", C.c_float), ("ms_cse_total", C.c_float), ("ms_total", C.c_float),
+    ]
+
+    def as_dict(self) -> dict:
+        d = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            if name in ("sort_m", "sort_passes"):
+                v = [int(x) for x in v][: int(self.sort_rounds)]
+            d[name] = v
+        return d
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libbce_gpu.so; raise (never fall back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise BceGpuError(-7, f"{_LIB_PATH} not built: run `python -m bce_b200.build` (needs nvcc)")
+    lib = C.CDLL(str(_LIB_PATH))
+    vp, u32, u32p = C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)
+    lib.bce_gpu_open.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.bce_gpu_close.argtypes = [vp]
+    lib.bce_gpu_close.restype = None
+    lib.bce_gpu_error_string.argtypes = [C.c_int]
+    lib.bce_gpu_error_string.restype = C.c_char_p
+    lib.bce_gpu_last_error.argtypes = [vp]
+    lib.bce_gpu_last_error.restype = C.c_char_p
+    lib.bce_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.bce_gpu_set_scratch_limit.argtypes = [vp, C.c_size_t]
+    lib.bce_gpu_bwt.argtypes = [vp, vp, u32, vp, u32p, vp]
+    lib.bce_gpu_wavelet.argtypes = [vp, vp, u32, C.POINTER(vp), u32p]
+    lib.bce_gpu_cse_begin.argtypes = [vp, vp, u32, u32p]
+    lib.bce_gpu_cse_next.argtypes = [vp, C.POINTER(CseBatch)]
+    lib.bce_gpu_compress_front.argtypes = [vp, vp, u32, u32p, u32p]
+    lib.bce_gpu_stage_input.argtypes = [vp, vp, u32]
+    lib.bce_gpu_front_resident.argtypes = [vp, u32p, C.POINTER(C.c_uint64)]
+    lib.bce_gpu_unbwt.argtypes = [vp, C.POINTER(vp), u32, u32, vp]
+    _lib = lib
+    return lib
+
+
+def _as_u8(data) -> np.ndarray:
+    if isinstance(data, (bytes, bytearray, memoryview)):
+        return np.frombuffer(data, dtype=np.uint8)
+    a = np.ascontiguousarray(data)
+    if a.dtype != np.uint8:
+        raise TypeError("expected bytes or a uint8 array")
+    return a
+
+
+class Frontend:
+    """One context per GPU (mirrors bce_gpu_open / bce_gpu_close)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.bce_gpu_open(device, C.byref(h))
+        if rc != 0:
+            raise BceGpuError(rc, "bce_gpu_open")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bce_gpu_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise BceGpuError(rc, self.lib.bce_gpu_last_error(self.h).decode(errors="replace"))
+
+    # -- stage A ------------------------------------------------------------------------
+    def bwt(self, data, want_sa: bool = False):
+        T = _as_u8(data)
+        n = T.size
+        L = np.empty(n, dtype=np.uint8)
+        sa = np.empty(n, dtype=np.uint32) if want_sa else None
+        off = C.c_uint32()
+        self._check(self.lib.bce_gpu_bwt(self.h, T.ctypes.data, n, L.ctypes.data, C.byref(off),
+                                         sa.ctypes.data if want_sa else None))
+        return L, int(off.value), sa
+
+    # -- stage B ------------------------------------------------------------------------
+    def wavelet(self, L=None, n: int | None = None):
+        if L is not None:
+            L = _as_u8(L)
+            n = L.size
+        words = n // 32 + 1
+        ranks = [np.empty(words, dtype=np.uint64) for _ in range(8)]
+        ptrs = (C.c_void_p * 8)(*[r.ctypes.data for r in ranks])
+        Cv = (C.c_uint32 * 8)()
+        self._check(self.lib.bce_gpu_wavelet(self.h, L.ctypes.data if L is not None else None, n, ptrs, Cv))
+        return ranks, [int(x) for x in Cv]
+
+    def _drain(self):
+        streams = [[] for _ in range(8)]
+        batch = CseBatch()
+        batches = 0
+        while True:
+            self._check(self.lib.bce_gpu_cse_next(self.h, C.byref(batch)))
+            batches += 1
+            for i in range(8):
+                cnt = int(batch.count[i])
+                if cnt:
+                    addr = C.addressof(batch.tuples[i].contents)
+                    arr = np.ctypeslib.as_array((C.c_uint32 * (cnt * 5)).from_address(addr)).reshape(cnt, 5)
+                    streams[i].append(arr.copy())
+            if batch.done:
+                break
+        out = [np.concatenate(s) if s else np.zeros((0, 5), dtype=np.uint32) for s in streams]
+        return out, batches
+
+    def cse(self, L=None, n: int | None = None):
+        """Returns (C[8], streams[8]); stream i is an (E_i, 5) uint32 array of set() arguments."""
+        if L is not None:
+            L = _as_u8(L)
+            n = L.size
+        Cv = (C.c_uint32 * 8)()
+        self._check(self.lib.bce_gpu_cse_begin(self.h, L.ctypes.data if L is not None else None, n, Cv))
+        streams, _ = self._drain()
+        return [int(x) for x in Cv], streams
+
+    def compress_front(self, data):
+        """BWT + wavelet + CSE with the BWT staying on the device."""
+        T = _as_u8(data)
+        off = C.c_uint32()
+        Cv = (C.c_uint32 * 8)()
+        self._check(self.lib.bce_gpu_compress_front(self.h, T.ctypes.data, T.size, C.byref(off), Cv))
+        streams, _ = self._drain()
+        return int(off.value), [int(x) for x in Cv], streams
+
+    def compress_front_discard(self, data):
+        """Same call sequence as compress_front, but the emitted counts are only touched in
+        pinned memory, not copied again (bench e2e leg).  Returns (offset, total counts)."""
+        T = _as_u8(data)
+        off = C.c_uint32()
+        Cv = (C.c_uint32 * 8)()
+        self._check(self.lib.bce_gpu_compress_front(self.h, T.ctypes.data, T.size, C.byref(off), Cv))
+        batch = CseBatch()
+        total = 0
+        while True:
+            self._check(self.lib.bce_gpu_cse_next(self.h, C.byref(batch)))
+            total += sum(int(batch.count[i]) for i in range(8))
+            if batch.done:
+                break
+        return int(off.value), total
+
+    # -- device-resident measurement -------------------------------------------------------
+    def stage_input(self, data):
+        T = _as_u8(data)
+        self._check(self.lib.bce_gpu_stage_input(self.h, T.ctypes.data, T.size))
+
+    def front_resident(self):
+        off = C.c_uint32()
+        tup = C.c_uint64()
+        self._check(self.lib.bce_gpu_front_resident(self.h, C.byref(off), C.byref(tup)))
+        return int(off.value), int(tup.value)
+
+    # -- inverse --------------------------------------------------------------------------
+    def unbwt(self, ranks, offset: int, n: int) -> np.ndarray:
+        ranks = [np.ascontiguousarray(r, dtype=np.uint64) for r in ranks]
+        ptrs = (C.c_void_p * 8)(*[r.ctypes.data for r in ranks])
+        out = np.empty(n, dtype=np.uint8)
+        self._check(self.lib.bce_gpu_unbwt(self.h, ptrs, offset, n, out.ctypes.data))
+        return out
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self.lib.bce_gpu_get_stats(self.h, C.byref(s)))
+        return s.as_dict()
+
+    def set_scratch_limit(self, nbytes: int):
+        self._check(self.lib.bce_gpu_set_scratch_limit(self.h, nbytes))

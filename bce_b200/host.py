@@ -1,0 +1,116 @@
+"""ctypes binding of include/bce_host.h (libbce_host.so): host range coders + archive writer."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from .gpu import CseBatch, Tuple5
+
+_LIB_PATH = Path(__file__).resolve().parent / "libbce_host.so"
+_lib = None
+
+HOST_SYMBOLS = [
+    "bce_archive_begin", "bce_archive_feed", "bce_archive_finish", "bce_archive_abort",
+    "bce_scan_begin", "bce_scan_feed", "bce_scan_finish", "bce_compress_buffer", "bce_scan_buffer",
+    "bce_host_default_config", "bce_host_free",
+]
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise RuntimeError(f"{_LIB_PATH} not built: run `python -m bce_b200.build`")
+        lib = C.CDLL(str(_LIB_PATH))
+        vp = C.c_void_p
+        lib.bce_archive_begin.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), vp]
+        lib.bce_archive_begin.restype = vp
+        lib.bce_archive_feed.argtypes = [vp, C.POINTER(CseBatch), C.c_int]
+        lib.bce_archive_finish.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        lib.bce_archive_abort.argtypes = [vp]
+        lib.bce_scan_begin.restype = vp
+        lib.bce_scan_feed.argtypes = [vp, C.POINTER(CseBatch)]
+        lib.bce_scan_finish.argtypes = [vp, vp]
+        lib.bce_compress_buffer.argtypes = [vp, vp, C.c_uint32, vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        lib.bce_scan_buffer.argtypes = [vp, vp, C.c_uint32, vp]
+        lib.bce_host_default_config.restype = vp
+        lib.bce_host_free.argtypes = [vp]
+        _lib = lib
+    return _lib
+
+
+def _batch_from(streams, done=True):
+    keep = [np.ascontiguousarray(s, dtype=np.uint32) for s in streams]
+    b = CseBatch()
+    for i, a in enumerate(keep):
+        b.count[i] = a.shape[0]
+        if a.shape[0]:
+            b.tuples[i] = C.cast(a.ctypes.data, C.POINTER(Tuple5))
+    b.done = 1 if done else 0
+    return b, keep
+
+
+def encode_archive(Cvals, streams, n: int, offset: int, cfg: bytes | None = None, threads: int = 1,
+                   pieces: int = 1) -> bytes:
+    """Host archive writer over given count streams (optionally fed in `pieces` batches)."""
+    lib = load_library()
+    Cv = (C.c_uint32 * 8)(*Cvals)
+    cfgbuf = np.frombuffer(cfg, dtype=np.uint8) if cfg is not None else None
+    w = lib.bce_archive_begin(n, Cv, cfgbuf.ctypes.data if cfgbuf is not None else None)
+    if not w:
+        raise RuntimeError("bce_archive_begin failed")
+    for p in range(pieces):
+        part = [s[(s.shape[0] * p) // pieces:(s.shape[0] * (p + 1)) // pieces] for s in streams]
+        b, keep = _batch_from(part, done=(p == pieces - 1))
+        rc = lib.bce_archive_feed(w, C.byref(b), threads)
+        assert rc == 0
+    words = C.c_void_p()
+    nw = C.c_size_t()
+    rc = lib.bce_archive_finish(w, offset, C.byref(words), C.byref(nw))
+    if rc != 0:
+        raise RuntimeError(f"bce_archive_finish failed: {rc}")
+    out = C.string_at(words.value, nw.value * 2)
+    lib.bce_host_free(words)
+    return out
+
+
+def scan_config(streams) -> bytes:
+    lib = load_library()
+    s = lib.bce_scan_begin()
+    b, keep = _batch_from(streams)
+    lib.bce_scan_feed(s, C.byref(b))
+    out = np.zeros(288, dtype=np.uint8)
+    rc = lib.bce_scan_finish(s, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"bce_scan_finish failed: {rc}")
+    return out.tobytes()
+
+
+def default_config() -> bytes:
+    return C.string_at(load_library().bce_host_default_config(), 288)
+
+
+def compress(frontend, data, cfg: bytes | None = None, threads: int = 8) -> bytes:
+    """Whole `bce -c` pipeline on a buffer: GPU front end + host coders."""
+    lib = load_library()
+    T = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data)
+    cfgbuf = np.frombuffer(cfg, dtype=np.uint8) if cfg is not None else None
+    words = C.c_void_p()
+    nw = C.c_size_t()
+    rc = lib.bce_compress_buffer(frontend.h, T.ctypes.data, T.size,
+                                 cfgbuf.ctypes.data if cfgbuf is not None else None, threads,
+                                 C.byref(words), C.byref(nw))
+    frontend._check(rc)
+    out = C.string_at(words.value, nw.value * 2)
+    lib.bce_host_free(words)
+    return out
+
+
+def scan(frontend, data) -> bytes:
+    lib = load_library()
+    T = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data)
+    out = np.zeros(288, dtype=np.uint8)
+    frontend._check(lib.bce_scan_buffer(frontend.h, T.ctypes.data, T.size, out.ctypes.data))
+    return out.tobytes()

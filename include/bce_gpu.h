@@ -1,0 +1,143 @@
+/*
+ * bce_gpu.h -- C ABI of the B200 compression front end for BCE v0.4.
+ *
+ * This is the drop-in boundary.  The reference (akamiru/bce) has no
+ * runtime plugin interface; its seams are the libdivsufsort C API and the
+ * policy_coder / policy_unbwt template parameters of BCE<> (bce.cpp:1111).  Each
+ * entry point below names the reference interface it replaces.  INTEGRATION.md shows
+ * the few lines a maintainer adds to bce.cpp to bind them.
+ *
+ * Conventions: plain pointers and sizes, no C++ / torch types; the caller owns every
+ * buffer it passes; functions return 0 or a negative BCE_GPU_E_* code (never throw,
+ * never exit); one context per GPU; a context is not thread-safe; all host pointers
+ * may be pageable or pinned memory.  Domain: 1 <= n < 2^31 (bce.cpp:374, saidx_t).
+ *
+ * There is no CPU fallback behind this header: every function runs CUDA kernels for
+ * sm_100a and fails with BCE_GPU_E_NODEVICE / BCE_GPU_E_CUDA when it cannot.
+ */
+#ifndef BCE_GPU_H
+#define BCE_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCE_GPU_ABI_VERSION 1
+
+enum {
+  BCE_GPU_OK = 0,
+  BCE_GPU_E_ARG = -1,        /* bad argument (NULL, n == 0, n >= 2^31, ...) */
+  BCE_GPU_E_NOMEM = -2,      /* host or device allocation failed */
+  BCE_GPU_E_CUDA = -3,       /* a CUDA call or kernel failed; see bce_gpu_last_error */
+  BCE_GPU_E_STATE = -4,      /* call sequence violated (e.g. cse_next before cse_begin) */
+  BCE_GPU_E_FRONTIER = -5,   /* CSE node frontier outgrew the device memory set aside for it */
+  BCE_GPU_E_INTERNAL = -6,   /* internal consistency check failed (watchdog, invariant) */
+  BCE_GPU_E_NODEVICE = -7    /* no usable CUDA device */
+};
+
+typedef struct bce_gpu_ctx bce_gpu_ctx;
+
+/* One emitted count = the five arguments of policy_coder::set(s, k, c1, c2, cs) at the
+ * reference's only call site, bce.cpp:1302:  (_0x0 - min, max - min + 1, _0x, _x1, _x). */
+typedef struct bce_tuple {
+  uint32_t sym, k, c1, c2, cs;
+} bce_tuple;
+
+/* A batch of emitted counts.  tuples[i] points into pinned host memory owned by the
+ * context and stays valid until the next bce_gpu_cse_next / cse_begin / close.
+ * Stream i = wavelet level i = coder_[i] (bce.cpp:1124).  Concatenating the batches of
+ * one stream gives exactly the sequence of set() calls the reference makes on coder_[i]:
+ * ascending round of the do..while (bce.cpp:1246), ascending position inside a round. */
+typedef struct bce_cse_batch {
+  const bce_tuple *tuples[8];
+  size_t count[8];
+  int done;                  /* 1 = the level loop terminated (bce.cpp:1371), no more batches */
+} bce_cse_batch;
+
+/* Counters and device timings of the last front-end call (bench / roofline input). */
+typedef struct bce_gpu_stats {
+  uint32_t n;
+  uint32_t sort_rounds;          /* prefix-doubling rounds, round 0 = initial 8-byte sort */
+  uint64_t sort_m[48];           /* elements sorted in round r */
+  uint32_t sort_passes[48];      /* radix passes run in round r */
+  uint64_t radix_launches;       /* onesweep pass launches in total */
+  uint64_t radix_elems;          /* sum over those launches of elements moved */
+  uint64_t cse_visits;           /* node visits (8(n-1) for primitive input) */
+  uint64_t cse_tuples;           /* emitted counts, all streams */
+  uint64_t cse_rounds;           /* rounds of the level loop */
+  uint64_t cse_launches;         /* launches of the level-loop kernel */
+  uint64_t cse_peak_frontier;    /* max nodes in one round, all levels */
+  uint64_t gpu_launches;         /* kernels launched by the last call */
+  float ms_h2d, ms_d2h;          /* host<->device copies */
+  float ms_pack, ms_radix, ms_rerank, ms_rekey, ms_bwt_gather;   /* stage A (BWT) */
+  float ms_wavelet, ms_cse;                                       /* stage B */
+  float ms_unbwt_bytes, ms_unbwt_chase;                           /* inverse */
+  float ms_bwt_total, ms_cse_total, ms_total;
+} bce_gpu_stats;
+
+/* ---- lifecycle ---------------------------------------------------------------- */
+int bce_gpu_open(int device, bce_gpu_ctx **out);
+void bce_gpu_close(bce_gpu_ctx *ctx);
+int bce_gpu_abi_version(void);
+const char *bce_gpu_error_string(int code);
+const char *bce_gpu_last_error(const bce_gpu_ctx *ctx);
+int bce_gpu_get_stats(const bce_gpu_ctx *ctx, bce_gpu_stats *out);
+/* cap on the scratch arena in bytes (0 = default: a share of free device memory) */
+int bce_gpu_set_scratch_limit(bce_gpu_ctx *ctx, size_t bytes);
+
+/* ---- stage A: suffix sort / BWT ------------------------------------------------
+ * Replaces File::rotate (bce.cpp:858-894) and File::bwt with its divbwt call into
+ * libdivsufsort (bce.cpp:896-910, call :901, splice :902).
+ *   L_out[r]   = T[(SA[r] - 1) mod n], rows = cyclic rotations of T in sorted order
+ *   offset_out = SA[0] = smallest start index of a least rotation  (File::offset_)
+ *   SA_out     = optional (may be NULL), n entries; identical rotations by ascending index
+ * The BWT also stays resident on the device for a following bce_gpu_cse_begin(L=NULL). */
+int bce_gpu_bwt(bce_gpu_ctx *ctx, const uint8_t *T, uint32_t n,
+                uint8_t *L_out, uint32_t *offset_out, uint32_t *SA_out);
+
+/* ---- stage B1: wavelet matrix ---------------------------------------------------
+ * Replaces the RankFile constructor body (bce.cpp:944-972) and Rank::build (:138-145).
+ * L = BWT bytes on the host, or NULL to use the BWT left on the device by bce_gpu_bwt.
+ * ranks_out (optional): 8 host arrays of n/32+1 words in the layout of Rank::rank_
+ * (bce.cpp:149: [32 data bits | 32-bit cumulative rank]).  C_out[i] = zeros of level
+ * (i+7)%8 as computed by BCE::encode (bce.cpp:1128). */
+int bce_gpu_wavelet(bce_gpu_ctx *ctx, const uint8_t *L, uint32_t n,
+                    uint64_t *const ranks_out[8], uint32_t C_out[8]);
+
+/* ---- stage B2: CSE level loop ---------------------------------------------------
+ * Replaces BCE::code(mode = 1) (bce.cpp:1236-1373) including its pArray queues
+ * (:226-356) and the root set-up in BCE::encode (:1124-1130, :1238-1240).
+ * cse_begin builds the wavelet matrix (as bce_gpu_wavelet) and the root frontier;
+ * cse_next runs rounds on the device and hands back the next batch of emitted counts. */
+int bce_gpu_cse_begin(bce_gpu_ctx *ctx, const uint8_t *L, uint32_t n, uint32_t C_out[8]);
+int bce_gpu_cse_next(bce_gpu_ctx *ctx, bce_cse_batch *out);
+
+/* ---- fused front end -------------------------------------------------------------
+ * bce_gpu_bwt + bce_gpu_cse_begin without the BWT leaving the device: what
+ * `RankFile file{...}` (bce.cpp:1411) plus the start of BCE::encode do.  Follow with
+ * bce_gpu_cse_next until done. */
+int bce_gpu_compress_front(bce_gpu_ctx *ctx, const uint8_t *T, uint32_t n,
+                           uint32_t *offset_out, uint32_t C_out[8]);
+
+/* ---- device-resident variant (measurement) ---------------------------------------
+ * stage_input copies T to the device; front_resident then runs stage A + B entirely in
+ * HBM (counts are written to device memory, nothing crosses PCIe) and returns the number
+ * of emitted counts.  Used for the `value` leg of bench.py. */
+int bce_gpu_stage_input(bce_gpu_ctx *ctx, const uint8_t *T, uint32_t n);
+int bce_gpu_front_resident(bce_gpu_ctx *ctx, uint32_t *offset_out, uint64_t *tuples_out);
+
+/* ---- inverse --------------------------------------------------------------------
+ * Replaces unbwt::bytewise::unbwt (bce.cpp:1043-1103): wavelet -> bytes (:1050-1085),
+ * inverse_bw_transform(..., idx = 1) from libdivsufsort (:1091), rotate by offset (:1093).
+ * ranks: 8 host arrays of n/32+1 words, layout of bce.cpp:149, as they are after
+ * Rank::finalize (:187-194): both the data bits and the cumulative ranks are read. */
+int bce_gpu_unbwt(bce_gpu_ctx *ctx, const uint64_t *const ranks[8],
+                  uint32_t offset, uint32_t n, uint8_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,84 @@
+"""Stage-by-stage GPU self test with verbose diagnostics (run by hand under gpurun while
+bringing kernels up; pytest -m gpu is the judged suite)."""
+import sys
+import time
+import traceback
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np  # noqa: E402
+
+from bce_b200 import Frontend, synth  # noqa: E402
+from oracle import oracle  # noqa: E402
+from tests.inputs import medium_cases, small_cases  # noqa: E402
+
+
+def diff(a, b):
+    a = np.asarray(a).reshape(-1)
+    b = np.asarray(b).reshape(-1)
+    if a.shape != b.shape:
+        return f"shape {a.shape} vs {b.shape}"
+    d = np.nonzero(a != b)[0]
+    return None if d.size == 0 else f"{d.size} diffs, first@{int(d[0])} got {a[d[0]]} want {b[d[0]]}"
+
+
+def main():
+    fe = Frontend(0)
+    bad = 0
+    cases = small_cases() + medium_cases()
+    if len(sys.argv) > 1:
+        cases = [c for c in cases if any(k in c[0] for k in sys.argv[1:])]
+    for name, data, prim in cases:
+        n = len(data)
+        msgs = []
+        try:
+            Lo, offo, sao = oracle.bwt(data, want_sa=True)
+            ro = oracle.wavelet(Lo)
+            want = oracle.cse(ro, n)
+            t = time.time()
+            try:
+                L, off, sa = fe.bwt(data, want_sa=True)
+                st = fe.stats()
+                if off != offo: msgs.append(f"offset {off} != {offo}")
+                for nm, x, y in (("L", L, Lo), ("SA", sa, sao)):
+                    d = diff(x, y)
+                    if d: msgs.append(f"{nm}: {d}")
+                msgs.append(f"[bwt rounds={st['sort_rounds']} m={st['sort_m']} P={st['sort_passes']}]")
+            except Exception as e:
+                msgs.append(f"BWT EXC {e}")
+            try:
+                ranks, Cv = fe.wavelet(Lo)
+                for j in range(8):
+                    d = diff(ranks[j], ro[j])
+                    if d: msgs.append(f"rank[{j}]: {d}")
+                if Cv != want["C"]: msgs.append(f"C {Cv} != {want['C']}")
+            except Exception as e:
+                msgs.append(f"WAVELET EXC {e}")
+            try:
+                Cv, streams = fe.cse(Lo)
+                st = fe.stats()
+                for i in range(8):
+                    d = diff(streams[i], want["streams"][i])
+                    if d: msgs.append(f"stream[{i}]: {d}")
+                if st["cse_visits"] != sum(want["visits"]): msgs.append(f"visits {st['cse_visits']} != {sum(want['visits'])}")
+                if st["cse_rounds"] != want["rounds"]: msgs.append(f"rounds {st['cse_rounds']} != {want['rounds']}")
+                msgs.append(f"[cse rounds={st['cse_rounds']} E={st['cse_tuples']} ms={st['ms_cse']:.2f}]")
+            except Exception as e:
+                msgs.append(f"CSE EXC {e}")
+            if prim:
+                try:
+                    out = fe.unbwt(ro, offo, n)
+                    if out.tobytes() != data: msgs.append("unbwt: " + str(diff(out, np.frombuffer(data, dtype=np.uint8))))
+                except Exception as e:
+                    msgs.append(f"UNBWT EXC {e}")
+        except Exception:
+            msgs.append(traceback.format_exc())
+        fails = [m for m in msgs if not m.startswith("[")]
+        bad += bool(fails)
+        print(("FAIL " if fails else "ok   ") + f"{name} n={n}: " + " | ".join(msgs), flush=True)
+    print("SELFTEST", "FAILED" if bad else "PASSED", bad)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

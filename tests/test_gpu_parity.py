@@ -1,0 +1,104 @@
+"""GPU parity tests proper: every stage of the CUDA path, called through the C ABI
+(include/bce_gpu.h via bce_b200.gpu), against the CPU oracle on the same seeded inputs.
+Bit-exact is the bar: integers, bytes and indices only on this path."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests.inputs import medium_cases, small_cases
+
+pytestmark = pytest.mark.gpu
+
+CASES = small_cases() + medium_cases()
+IDS = [c[0] for c in CASES]
+
+
+def first_diff(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    if a.shape != b.shape:
+        return f"shape {a.shape} vs {b.shape}"
+    d = np.nonzero(a.reshape(-1) != b.reshape(-1))[0]
+    if d.size == 0:
+        return None
+    i = int(d[0])
+    return f"{d.size} mismatches, first at flat index {i}: got {a.reshape(-1)[i]} want {b.reshape(-1)[i]}"
+
+
+@pytest.mark.parametrize("name,data,primitive", CASES, ids=IDS)
+def test_bwt_offset_sa(frontend, name, data, primitive):
+    L, off, sa = frontend.bwt(data, want_sa=True)
+    Lo, offo, sao = oracle.bwt(data, want_sa=True)
+    assert off == offo
+    assert first_diff(L, Lo) is None, first_diff(L, Lo)
+    assert first_diff(sa, sao) is None, first_diff(sa, sao)
+    st = frontend.stats()
+    assert st["sort_rounds"] >= 1 and st["sort_m"][0] == len(data)
+
+
+@pytest.mark.parametrize("name,data,primitive", CASES, ids=IDS)
+def test_wavelet_ranks(frontend, name, data, primitive):
+    Lo, _, _ = oracle.bwt(data)
+    ranks, Cv = frontend.wavelet(Lo)
+    ro = oracle.wavelet(Lo)
+    for j in range(8):
+        assert first_diff(ranks[j], ro[j]) is None, (j, first_diff(ranks[j], ro[j]))
+    n = len(data)
+    zeros = [n - (int(r[n // 32]) & 0xFFFFFFFF) - bin((int(r[n // 32]) >> 32) & ((1 << (n % 32)) - 1)).count("1") for r in ro]
+    assert Cv == [zeros[(i + 7) % 8] for i in range(8)]
+
+
+@pytest.mark.parametrize("name,data,primitive", CASES, ids=IDS)
+def test_cse_streams(frontend, name, data, primitive):
+    Lo, _, _ = oracle.bwt(data)
+    want = oracle.cse(oracle.wavelet(Lo), len(data))
+    Cv, streams = frontend.cse(Lo)
+    assert Cv == want["C"]
+    for i in range(8):
+        assert first_diff(streams[i], want["streams"][i]) is None, (i, first_diff(streams[i], want["streams"][i]))
+    st = frontend.stats()
+    assert st["cse_visits"] == sum(want["visits"])
+    assert st["cse_rounds"] == want["rounds"]
+    if primitive and len(data) > 1:
+        assert st["cse_visits"] == 8 * (len(data) - 1)
+
+
+@pytest.mark.parametrize("name,data,primitive", CASES, ids=IDS)
+def test_fused_front_archive(frontend, name, data, primitive):
+    """fused call -> counts -> archive writer == the oracle's `bce -c` archive (KATs included)."""
+    off, Cv, streams = frontend.compress_front(data)
+    got = oracle.encode_archive(Cv, streams, len(data), off)
+    assert got == oracle.compress(data)
+
+
+@pytest.mark.parametrize("name,data,primitive", CASES, ids=IDS)
+def test_unbwt(frontend, name, data, primitive):
+    if not primitive:
+        pytest.skip("the reference does not round-trip exact powers (SURVEY.md 4-6)")
+    Lo, off, _ = oracle.bwt(data)
+    ranks = oracle.wavelet(Lo)
+    out = frontend.unbwt(ranks, off, len(data))
+    assert out.tobytes() == data
+    if len(data) <= 40000:
+        assert first_diff(out, oracle.unbwt_bitwise(ranks, off, len(data))) is None
+
+
+def test_small_emission_buffers_force_draining(frontend, monkeypatch):
+    """Several cse_next batches must concatenate to the same streams."""
+    from bce_b200 import synth
+    data = synth.generate("markov2-text", 400_000, 3).tobytes()
+    Lo, _, _ = oracle.bwt(data)
+    want = oracle.cse(oracle.wavelet(Lo), len(data))
+    monkeypatch.setenv("BCE_GPU_PINNED_LIMIT", str(8 * 20 * 210_000))
+    Cv, streams = frontend.cse(Lo)
+    for i in range(8):
+        assert first_diff(streams[i], want["streams"][i]) is None, i
+
+
+def test_resident_matches_hosted(frontend):
+    from bce_b200 import synth
+    data = synth.generate("enwik-shaped", 500_000, 5).tobytes()
+    off, Cv, streams = frontend.compress_front(data)
+    frontend.stage_input(data)
+    off2, tuples = frontend.front_resident()
+    assert off2 == off and tuples == sum(s.shape[0] for s in streams)

@@ -1,0 +1,69 @@
+"""CPU: the product's host half (libbce_host.so: range coders, archive writer, scan policy)
+against the oracle's archives and the golden fixtures.  No GPU involved: the count streams
+come from the oracle, exactly what the GPU path must deliver."""
+import hashlib
+import json
+from pathlib import Path
+
+import pytest
+
+from bce_b200 import host
+from oracle import oracle
+from tests.inputs import medium_cases, small_cases
+
+GOLD = Path(__file__).resolve().parent / "golden"
+CASES = small_cases() + medium_cases()[:3]
+IDS = [c[0] for c in CASES]
+
+
+def streams_of(data):
+    L, off, _ = oracle.bwt(data)
+    c = oracle.cse(oracle.wavelet(L), len(data))
+    return off, c
+
+
+def test_default_config_table():
+    assert host.default_config() == oracle.default_config()
+
+
+@pytest.mark.parametrize("name,data,primitive", CASES, ids=IDS)
+def test_archive_writer_bit_exact(name, data, primitive):
+    ref = {v["name"]: v for v in json.loads((GOLD / "ref_vectors.json").read_text())["vectors"]}[name]
+    off, c = streams_of(data)
+    for threads, pieces in ((1, 1), (8, 1), (8, 4)):
+        arc = host.encode_archive(c["C"], c["streams"], len(data), off, threads=threads, pieces=pieces)
+        assert hashlib.sha256(arc).hexdigest() == ref["archive_sha256"], (threads, pieces)
+
+
+def test_kat_archives_through_host_writer():
+    for v in json.loads((GOLD / "kat.json").read_text())["vectors"]:
+        data = eval(v["input_py"])
+        off, c = streams_of(data)
+        assert host.encode_archive(c["C"], c["streams"], len(data), off).hex() == v["archive_hex"]
+
+
+def test_scan_config_and_archive_with_config():
+    g = json.loads((GOLD / "scan_markov2_200k.json").read_text())
+    data = dict((c[0], c[1]) for c in medium_cases())[g["input"]]
+    off, c = streams_of(data)
+    cfg = host.scan_config(c["streams"])
+    assert cfg.hex() == g["config_hex"]                      # bit-exact `bce -s` output
+    arc = host.encode_archive(c["C"], c["streams"], len(data), off, cfg=cfg)
+    assert len(arc) == g["archive_bytes"] and hashlib.sha256(arc).hexdigest() == g["archive_with_config_sha256"]
+    assert arc == oracle.encode_archive(c["C"], c["streams"], len(data), off, cfg=cfg)
+
+
+def test_wide_ranges_take_the_binary_decomposition():
+    """k > 31 symbols (bce.cpp:507-510) and uint32 wrap in the context index (:674)."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    streams = []
+    for i in range(8):
+        k = rng.integers(2, 5000, size=400, dtype=np.uint32)
+        s = (rng.integers(0, 1 << 30, size=400, dtype=np.uint32) % k).astype(np.uint32)
+        cs = rng.integers(2, 1 << 31, size=400, dtype=np.uint32)
+        c1 = (rng.integers(0, 1 << 31, size=400, dtype=np.uint32) % cs).astype(np.uint32)
+        c2 = (rng.integers(0, 1 << 31, size=400, dtype=np.uint32) % cs).astype(np.uint32)
+        streams.append(np.stack([s, k, c1, c2, cs], axis=1).astype(np.uint32))
+    Cv = [5] * 8
+    assert host.encode_archive(Cv, streams, 1000, 3) == oracle.encode_archive(Cv, streams, 1000, 3)

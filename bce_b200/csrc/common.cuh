@@ -17,6 +17,8 @@ constexpr int kSMsB200 = 148;
 // ---------------------------------------------------------------------------------
 struct Ctx;
 void set_error(Ctx* c, const char* fmt, ...);
+bool trace_on();
+#define BCE_TRACE(...) do { if (bce::trace_on()) { fprintf(stderr, "[bce_gpu] " __VA_ARGS__); fputc('\n', stderr); fflush(stderr); } } while (0)
 
 #define BCE_CUDA(ctx, call)                                                         \
   do {                                                                              \
@@ -102,7 +104,7 @@ __device__ __forceinline__ uint64_t desc_load(const uint64_t* p) {
 
 // Spin until the descriptor carries `tag`.  The budget bounds the wait so that a logic
 // error surfaces as BCE_GPU_E_INTERNAL instead of a hung GPU.
-constexpr uint32_t kSpinBudget = 1u << 24;
+constexpr uint32_t kSpinBudget = 1u << 18;
 __device__ __forceinline__ uint64_t desc_wait(const uint64_t* p, uint32_t tag, uint32_t* err) {
   uint64_t w = desc_load(p);
   uint32_t spins = 0;

@@ -15,14 +15,14 @@
 //   the tiles of the level (warp-wide decoupled look-back, three carried values)
 //   -> write counts, zero-children and one-children at their exact ordered positions.
 // So the stable partition into the next level's halves and the emission order fall out of
-// prefix sums; no atomics decide any position.  grid.sync() separates rounds.
+// prefix sums; no atomics decide any position.  A grid-wide barrier separates rounds: a
+// monotonically increasing arrival counter (all CTAs are co-resident: cooperative launch) with a
+// bounded spin, so that a logic error surfaces as BCE_GPU_E_INTERNAL and never as a hung GPU.
 //
 // Algorithmic HBM bytes: 48 B per node visit + 20 B per emitted count.
-#include <cooperative_groups.h>
+#include <algorithm>
 
 #include "ctx.h"
-
-namespace cg = cooperative_groups;
 
 namespace bce {
 
@@ -30,7 +30,7 @@ constexpr int CS_THREADS = 256;
 constexpr int CS_ITEMS = 4;
 constexpr int CS_TILE = CS_THREADS * CS_ITEMS;
 
-enum : uint32_t { kCseRunning = 0, kCseDone = 1, kCseDrain = 2, kCseOverflow = 3 };
+enum : uint32_t { kCseRunning = 0, kCseDone = 1, kCseDrain = 2, kCseOverflow = 3, kCseRunaway = 4 };
 
 struct CseDeviceState {
   uint32_t cnt[2][8][2];                 // [round parity][level][half] frontier sizes
@@ -40,7 +40,9 @@ struct CseDeviceState {
   uint32_t round;
   uint32_t status;
   uint32_t err;                          // chained-scan watchdog
-  uint32_t pad;
+  uint32_t barrier_fail;                 // round at which the grid barrier timed out (+1), 0 = never
+  unsigned long long arrivals;           // grid barrier: total CTA arrivals since cse_begin
+  unsigned long long barriers;           // grid barriers completed since cse_begin (host-maintained between launches)
 };
 
 struct CseArgs {
@@ -55,6 +57,7 @@ struct CseArgs {
   uint64_t* desc;                        // 3 x desc_tiles
   uint32_t desc_tiles;
   uint32_t max_rounds;
+  uint32_t round_limit;                  // no input needs more than 8 n rounds: beyond it something is broken
   CseDeviceState* st;
 };
 
@@ -79,6 +82,33 @@ __device__ __forceinline__ unsigned long long vol_load64(const unsigned long lon
   return v;
 }
 
+// Grid-wide barrier.  Every CTA adds one arrival; barrier number b (0-based, counted since
+// cse_begin) is passed when the counter reaches (b + 1) * gridDim.x.  The counter only grows,
+// so there is no reset race.  Returns false (and records the failure) if the others do not
+// arrive within the spin budget.
+__device__ __forceinline__ bool grid_barrier(CseDeviceState* S, unsigned long long index, uint32_t round) {
+  __syncthreads();
+  bool ok = true;
+  if (threadIdx.x == 0) {
+    const unsigned long long target = (index + 1) * gridDim.x;
+    __threadfence();
+    atomicAdd(&S->arrivals, 1ull);
+    uint32_t spins = 0;
+    while (vol_load64(&S->arrivals) < target) {
+      if (++spins > (1u << 22)) {
+        atomicExch(&S->barrier_fail, round + 1);
+        atomicExch(&S->err, 2u);
+        ok = false;
+        break;
+      }
+      __nanosleep(20);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  return ok;
+}
+
 __global__ void cse_init_kernel(CseArgs a, uint32_t n) {
   // roots: node (0, C[i], n - C[i]) in the zero-half of level i when both are non-zero
   // (bce.cpp:1238-1240)
@@ -93,7 +123,8 @@ __global__ void cse_init_kernel(CseArgs a, uint32_t n) {
     S->cnt[1][i][0] = S->cnt[1][i][1] = 0;
     S->emitted[0][i] = S->emitted[1][i] = 0;
   }
-  if (i == 0) { S->visits = 0; S->peak_frontier = 0; S->round = 0; S->status = kCseRunning; S->err = 0; }
+  if (i == 0) { S->visits = 0; S->peak_frontier = 0; S->round = 0; S->status = kCseRunning; S->err = 0;
+                S->barrier_fail = 0; S->arrivals = 0; S->barriers = 0; }
 }
 
 __global__ void cse_reset_emitted_kernel(CseDeviceState* S) {
@@ -102,7 +133,6 @@ __global__ void cse_reset_emitted_kernel(CseDeviceState* S) {
 }
 
 __global__ void __launch_bounds__(CS_THREADS, 2) cse_rounds_kernel(CseArgs a) {
-  cg::grid_group grid = cg::this_grid();
   __shared__ uint64_t s_scan[CS_THREADS / 32];
   __shared__ uint32_t s_prefix[3];
   __shared__ uint32_t s_cnt[8][2];
@@ -114,6 +144,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_rounds_kernel(CseArgs a) {
   CseDeviceState* S = a.st;
   uint32_t round = vol_load(&S->round);
   uint32_t rounds_done = 0;
+  const unsigned long long barrier0 = vol_load64(&S->barriers);   // barriers passed by earlier launches
 
   for (;;) {
     const int cur = round & 1, nxt = cur ^ 1;
@@ -135,7 +166,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_rounds_kernel(CseArgs a) {
         if (s_emitted[l] + lvl > a.ecap[l]) drain = 1;   // a round emits at most one count per node
       }
       s_flags[0] = t;
-      s_flags[1] = nodes == 0 ? kCseDone : (drain ? kCseDrain : kCseRunning);
+      s_flags[1] = nodes == 0 ? kCseDone : (round >= a.round_limit ? kCseRunaway : (drain ? kCseDrain : kCseRunning));
       if (blockIdx.x == 0 && nodes && !drain && rounds_done < a.max_rounds) {
         S->visits += nodes;
         if (nodes > S->peak_frontier) S->peak_frontier = nodes;
@@ -145,7 +176,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_rounds_kernel(CseArgs a) {
     const uint32_t total_tiles = s_flags[0];
     const uint32_t decision = s_flags[1];
     if (decision != kCseRunning || rounds_done >= a.max_rounds) {
-      if (blockIdx.x == 0 && tid == 0) { S->status = decision; S->round = round; }
+      if (blockIdx.x == 0 && tid == 0) { S->status = decision; S->round = round; S->barriers = barrier0 + rounds_done; }
       break;
     }
     // levels without nodes hand an empty frontier (and their emission cursor) to the next round
@@ -297,11 +328,11 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_rounds_kernel(CseArgs a) {
       __syncthreads();        // s_prefix / s_scan are reused by the next tile
     }
 
-    grid.sync();
+    grid_barrier(S, barrier0 + rounds_done, round);
     ++round;
     ++rounds_done;
     if (vol_load(&S->status) != kCseRunning || vol_load(&S->err) != 0) {
-      if (blockIdx.x == 0 && tid == 0) S->round = round;
+      if (blockIdx.x == 0 && tid == 0) { S->round = round; S->barriers = barrier0 + rounds_done; }
       break;
     }
   }
@@ -364,6 +395,7 @@ int cse_begin(Ctx* c, uint32_t n) {
   a.cap = uint32_t(cap);
   a.desc_tiles = uint32_t(desc_tiles);
   a.max_rounds = 0x7FFFFFFFu;
+  a.round_limit = uint32_t(std::min<uint64_t>(uint64_t(n) * 8 + 64, 0xFFFFFFF0ull));
   a.st = reinterpret_cast<CseDeviceState*>(c->small.as<char>() + kSmallCse);
   static_assert(sizeof(CseDeviceState) <= 1024, "state must fit its slot in Ctx::small");
 
@@ -380,6 +412,7 @@ int cse_begin(Ctx* c, uint32_t n) {
   }
   c->cse_active = true;
   c->cse_done = false;
+  BCE_TRACE("cse_begin n=%u cap=%zu ecap=%zu grid=%d", n, cap, ecap, H->grid);
   return BCE_GPU_OK;
 }
 
@@ -394,6 +427,7 @@ int cse_advance(Ctx* c, bool resident, bce_cse_batch* out) {
 
   CseDeviceState* h_state = reinterpret_cast<CseDeviceState*>(c->pinned_small.as<char>() + 40 * 1024);
   BCE_CUDA(c, cudaEventRecord(c->ev[2], st));
+  BCE_TRACE("cse launch grid=%d cap=%u ecap=%llu", H->grid, H->args.cap, H->args.ecap[0]);
   void* kargs[] = {&H->args};
   BCE_CUDA(c, cudaLaunchCooperativeKernel((const void*)cse_rounds_kernel, dim3(H->grid), dim3(CS_THREADS),
                                           kargs, 0, st));
@@ -405,8 +439,19 @@ int cse_advance(Ctx* c, bool resident, bce_cse_batch* out) {
   float ms = 0;
   BCE_CUDA(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
   c->stats.ms_cse += ms;
+  BCE_TRACE("cse returned status=%u round=%u err=%u visits=%llu ms=%.3f", h_state->status, h_state->round,
+            h_state->err, h_state->visits, ms);
 
-  if (h_state->err) { set_error(c, "cse: chained-scan watchdog fired at round %u", h_state->round); return BCE_GPU_E_INTERNAL; }
+  if (h_state->err) {
+    set_error(c, "cse: %s watchdog fired (round %u, barrier_fail %u, arrivals %llu, barriers %llu, grid %d)",
+              h_state->err == 2 ? "grid-barrier" : "chained-scan", h_state->round, h_state->barrier_fail,
+              h_state->arrivals, h_state->barriers, H->grid);
+    return BCE_GPU_E_INTERNAL;
+  }
+  if (h_state->status == kCseRunaway) {
+    set_error(c, "cse: level loop still running after %u rounds (n = %u)", h_state->round, H->n);
+    return BCE_GPU_E_INTERNAL;
+  }
   if (h_state->status == kCseOverflow) {
     set_error(c, "cse: node frontier exceeded %u nodes per level at round %u", H->args.cap, h_state->round);
     return BCE_GPU_E_FRONTIER;
@@ -418,9 +463,13 @@ int cse_advance(Ctx* c, bool resident, bce_cse_batch* out) {
   const int par = h_state->round & 1;
   size_t total = 0, cnt[8];
   for (int l = 0; l < 8; ++l) { cnt[l] = size_t(h_state->emitted[par][l]); total += cnt[l]; }
+  if (h_state->status == kCseDrain && total == 0) {
+    set_error(c, "cse: kernel asked to drain empty emission buffers at round %u", h_state->round);
+    return BCE_GPU_E_INTERNAL;
+  }
   c->stats.cse_tuples += total;
   c->stats.cse_visits = h_state->visits;
-  c->stats.cse_rounds = h_state->round;
+  c->stats.cse_rounds = h_state->round ? h_state->round : 1;   // the reference's do..while runs at least once
   c->stats.cse_peak_frontier = h_state->peak_frontier;
 
   if (!resident && out) {

@@ -1,0 +1,145 @@
+// bce_main.cpp -- the `bce` command line tool with the reference's interface
+// (main, bce.cpp:1376-1484): same arguments, same messages, same exit codes, same archive
+// bytes -- but RankFile + BCE::code run on the GPU through include/bce_gpu.h.
+//
+//   bce -c archive.bce file [config.bcc]      compress
+//   bce -s config.bcc file                    scan: derive a coder config
+//   bce -d file archive.bce                   decompress   (see decode.hpp)
+//   bce -ds file archive.bce                  decompress, serial inverse BWT on the host
+//
+// There is no CPU fallback for the front end: without a usable sm_100 device the tool
+// reports the CUDA error and exits with -3.
+#include <chrono>
+#include <cinttypes>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "../../../include/bce_host.h"
+#include "coders.hpp"
+#ifdef BCE_HAVE_DECODER
+#include "decode.hpp"
+#endif
+
+namespace {
+
+bool slurp(const std::string& path, std::vector<uint8_t>& out) {        // File::File, bce.cpp:842-856
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) return false;
+  const std::streamoff size = f.tellg();
+  if (size < 0) return false;
+  out.resize(size_t(size));
+  f.seekg(0, std::ios::beg);
+  return size == 0 || bool(f.read(reinterpret_cast<char*>(out.data()), size));
+}
+
+int gpu_failure(bce_gpu_ctx* ctx, int rc) {
+  std::printf("GPU front end failed: %s (%s)\n", bce_gpu_error_string(rc), ctx ? bce_gpu_last_error(ctx) : "no context");
+  return rc;
+}
+
+void usage() {                                                           // bce.cpp:1474-1482
+  std::printf("Usage:\n");
+  std::printf("  bce -c archive.bce file [config.bcc]\n");
+  std::printf("   Compresses \"file\" to archive \"archive.bce\" [using config \"config.bcc\"]\n");
+  std::printf("\n");
+  std::printf("  bce -d file archive.bce\n");
+  std::printf("   Decompresses archive \"archive.bce\" to \"file\"\n");
+  std::printf("\n");
+  std::printf("  bce -s config.bcc file\n");
+  std::printf("   Scan \"file\" and generate a config file \"config.bcc\" to improve the AdaptiveCoder (uses a lot of memory)\n");
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  std::printf("BCE v0.4 Release (B200 front end)\n");
+  std::printf("Archive format and coders of BCE v0.4, Copyright (C) 2016  Christoph Diegelmann\n\n");
+
+  const bool flag = argc >= 2 && argv[1][0] == '-';
+  using clock = std::chrono::high_resolution_clock;
+
+  if (argc == 4 && flag && argv[1][1] == 's') {                          // bce.cpp:1384-1402
+    const auto start = clock::now();
+    std::vector<uint8_t> data;
+    if (!slurp(argv[3], data) || data.empty()) {
+      std::printf("Error loading file\n");
+      return -1;
+    }
+    bce_gpu_ctx* ctx = nullptr;
+    int rc = bce_gpu_open(0, &ctx);
+    if (rc) return gpu_failure(ctx, rc);
+    uint8_t cfg[288];
+    rc = bce_scan_buffer(ctx, data.data(), uint32_t(data.size()), cfg);
+    if (rc) { gpu_failure(ctx, rc); bce_gpu_close(ctx); return rc; }
+    bce_gpu_close(ctx);
+    bcehost::ConfigTable table;
+    std::memcpy(table.data(), cfg, 288);
+    bcehost::save_config_file(argv[2], table);
+    const std::chrono::duration<double> d = clock::now() - start;
+    std::printf("Scanned %" PRIuMAX " B in %.1f s\n", uintmax_t(data.size()), d.count());
+    return 0;
+  }
+
+  if ((argc == 4 || argc == 5) && flag && argv[1][1] == 'c') {           // bce.cpp:1403-1427
+    const auto start = clock::now();
+    bcehost::ConfigTable table = bcehost::default_config();
+    if (argc == 5) bcehost::load_config_file(argv[4], table);            // failure is non-fatal (:629-632)
+    std::vector<uint8_t> data;
+    if (!slurp(argv[3], data) || data.empty()) {
+      std::printf("Error loading file\n");
+      return -1;
+    }
+    bce_gpu_ctx* ctx = nullptr;
+    int rc = bce_gpu_open(0, &ctx);
+    if (rc) return gpu_failure(ctx, rc);
+    uint16_t* words = nullptr;
+    size_t nwords = 0;
+    rc = bce_compress_buffer(ctx, data.data(), uint32_t(data.size()),
+                             reinterpret_cast<const uint8_t*>(table.data()), 8, &words, &nwords);
+    if (rc) { gpu_failure(ctx, rc); bce_gpu_close(ctx); return rc; }
+    bce_gpu_close(ctx);
+    const std::chrono::duration<double> d = clock::now() - start;
+    std::printf("Compressed from %" PRIuMAX " B -> %zu B in %.1f s\n", uintmax_t(data.size()),
+                nwords * sizeof(uint16_t), d.count());
+    std::ofstream archive(argv[2], std::ios::binary | std::ios::trunc);
+    archive.write(reinterpret_cast<const char*>(words), std::streamsize(nwords * sizeof(uint16_t)));
+    bce_host_free(words);
+    return 0;
+  }
+
+  if (argc == 4 && flag && argv[1][1] == 'd') {                          // bce.cpp:1428-1472
+#ifdef BCE_HAVE_DECODER
+    const auto start = clock::now();
+    std::ifstream archive(argv[3], std::ios::binary | std::ios::ate);
+    const std::streamoff size = archive ? std::streamoff(archive.tellg()) : -1;
+    if (size < 0) {
+      std::printf("Archive not found.\n");
+      return -1;
+    }
+    archive.seekg(0, std::ios::beg);
+    std::vector<uint16_t> words(size_t(size) / sizeof(uint16_t));
+    if (size > 0 && !archive.read(reinterpret_cast<char*>(words.data()), size)) {
+      std::printf("Could not read Archive.\n");
+      return -2;
+    }
+    std::vector<uint8_t> out;
+    const int rc = bcehost::decode_archive(words, argv[1][2] == 's', out);
+    if (rc) return rc;
+    const std::chrono::duration<double> d = clock::now() - start;
+    std::printf("Decompressed from %zu B -> %zu B in %.1f s\n", size_t(size), out.size(), d.count());
+    std::ofstream file(argv[2], std::ios::binary | std::ios::trunc);
+    file.write(reinterpret_cast<const char*>(out.data()), std::streamsize(out.size()));
+    return 0;
+#else
+    std::printf("This build carries the compression front end only; decode with the reference's bce -d\n"
+                "(INTEGRATION.md shows its unbwt policy bound to bce_gpu_unbwt).\n");
+    return -4;
+#endif
+  }
+
+  usage();
+  return 0;
+}

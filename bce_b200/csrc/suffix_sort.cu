@@ -331,6 +331,7 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
       BCE_CUDA(c, cudaGetLastError());
       BCE_TRY(lap(S.ms_rekey));
     }
+    BCE_TRACE("sort round %d m=%u h=%llu tiebreak=%d passes<=%d", round, m, (unsigned long long)h, int(tiebreak), np);
     uint64_t* ks; uint32_t* vs; int ran = 0;
     BCE_TRY(radix_sort_pairs(c, kcur, kalt, vcur, valt, m, shifts, np, &ks, &vs, &ran));
     BCE_TRY(lap(S.ms_radix));

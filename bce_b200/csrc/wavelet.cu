@@ -147,6 +147,7 @@ __global__ void roots_kernel(const uint32_t* __restrict__ zeros, uint32_t* __res
 // Builds Ctx::ranks (8 x words) from Ctx::bwt.  Needs 2 x (n + 64) bytes of scratch.
 int wavelet_build(Ctx* c, uint32_t n) {
   cudaStream_t st = c->stream;
+  BCE_TRACE("wavelet_build n=%u", n);
   const size_t words = size_t(n) / 32 + 1;
   BCE_TRY(c->ranks.ensure(c, 8 * words * sizeof(uint64_t)));
   const size_t padded = (size_t(n) + 64 + 255) & ~size_t(255);

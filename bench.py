@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- BWT + CSE compression front end throughput on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one pass of the hot path (suffix sort/BWT + wavelet matrix + CSE level loop) over
+one synthetic input per GPU.  At N = 1 the workload is configs[1] of BASELINE.json: 100 MB of
+enwik-shaped synthetic text (10^8 bytes, > 126 MB L2 across its 12 n key/rank buffers, so no
+L2 flush is needed between steps).  At N > 1 every rank compresses its own file of the same
+generator (different seeds): replicas only, weak scaling, no data-path collective; one small
+all_gather of per-rank stats is the only traffic.
+
+Legs of the default arm:
+  value  input resident in HBM when the timed region starts; counts written to HBM.
+  e2e    the same through the C-ABI call a user makes, from pinned HOST memory, with the
+         emitted counts copied back to pinned host memory inside the timed region.
+  roofline     dominant kernel, algorithmic bytes / CUDA-event kernel time vs measured HBM peak.
+  cpu_baseline rank 0, N = 1: the UNMODIFIED reference front end (oracle/_ref, built from
+               /root/reference/bce.cpp with a recording coder) on a bounded sample.
+`--impl reference` times that reference front end alone on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "compress_MBps_bwt_cse"
+UNIT = "MB/s"
+WORKLOADS = {
+    # name: (generator, bytes, seed)
+    "markov2-1MB": ("markov2-text", 10**6, 1),
+    "enwik-100MB": ("enwik-shaped", 10**8, 2),
+    "enwik-1GB": ("enwik-shaped", 10**9, 3),
+    "mixed-256MB": ("mixed-binary", 268435456, 4),
+    "batch-128MB": ("enwik-shaped", 134217728, 100),
+}
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path
+# ---------------------------------------------------------------------------------------------
+def reference_front_seconds(sample, threads: int):
+    """Unmodified reference: RankFile ctor (rotate + BWT + wavelet) + BCE<tap>::encode (the CSE
+    loop, handing every count to a coder that stores the 5 words), through oracle/_ref."""
+    from oracle import oracle
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    r = oracle.ref_front(sample, want_bwt=False, want_ranks=False, record=True)
+    return r["seconds_rankfile"] + r["seconds_encode"], r
+
+
+def pick_sample_bytes(gen, seed, budget_s: float, threads: int):
+    """Probe on 1 MiB, then size the sample so that one step takes about budget_s seconds."""
+    from bce_b200 import synth
+    probe = synth.generate(gen, 1 << 20, seed)
+    t, _ = reference_front_seconds(probe, threads)
+    rate = (1 << 20) / max(t, 1e-3)                     # bytes per second, roughly size-independent
+    return int(max(1 << 20, min(64 << 20, rate * budget_s))), rate
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return 0
+    from bce_b200 import synth
+    from oracle import oracle
+    gen, nbytes, seed = WORKLOADS[args.workload]
+    if not oracle.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return 0
+    cores = os.cpu_count() or 1
+    threads = min(8, cores)                              # the reference forks over 8 levels at most (bce.cpp:1250)
+    budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    sample_bytes, _ = pick_sample_bytes(gen, seed, budget, threads)
+    sample = synth.generate(gen, sample_bytes, seed)
+    for _ in range(args.warmup):
+        reference_front_seconds(sample, threads)
+    times = []
+    for _ in range(args.steps):
+        t, r = reference_front_seconds(sample, threads)
+        times.append(t)
+    total = sum(times)
+    value = sample_bytes * args.steps / total / 1e6
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32",
+        "data": "synthetic", "gpu_launches": 0,
+        "config": {"workload": args.workload, "generator": gen, "bytes": nbytes, "seed": seed,
+                   "sample_bytes": sample_bytes},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                         "sample": f"first {sample_bytes} bytes of {args.workload}; unmodified bce.cpp front end "
+                                   f"(rotate+BWT+wavelet+CSE loop, counts stored by a tap coder); BWT stage is the "
+                                   f"oracle's SA-IS stand-in for libdivsufsort; OMP_NUM_THREADS={threads} of {cores} cores"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def algorithmic_bytes(st: dict) -> dict:
+    n = st["n"]
+    stage_a = 19 * n + sum((44 + 24 * p) * m for m, p in zip(st["sort_m"], st["sort_passes"]))
+    stage_b = 19 * n + 48 * st["cse_visits"] + 20 * st["cse_tuples"]
+    return {"stage_a": stage_a, "stage_b": stage_b, "total": stage_a + stage_b}
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from bce_b200 import Frontend, batch, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    gen, nbytes, seed = WORKLOADS[args.workload]
+    if args.bytes:
+        nbytes = args.bytes
+    my_seed = seed + rank                                  # one independent file per GPU
+    data = synth.generate(gen, nbytes, my_seed)
+    pinned = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = data
+    host_in = pinned.numpy()
+
+    fe = Frontend(local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def maxreduce(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value leg: device resident ----------------------------------------------------------
+    fe.stage_input(host_in)
+    for _ in range(args.warmup):
+        fe.front_resident()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms, stats_list = 0.0, []
+    for _ in range(args.steps):
+        fe.front_resident()
+        st = fe.stats()
+        dev_ms += st["ms_total"]
+        stats_list.append(st)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    dev_ms = maxreduce(dev_ms)
+    wall_ms = maxreduce(wall_ms)
+    st = stats_list[-1]
+    value = world * nbytes * args.steps / (dev_ms / 1e3) / 1e6
+
+    # ---- e2e leg: host buffers through the C ABI -----------------------------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        fe.compress_front_discard(host_in)
+    barrier()
+    t0 = time.perf_counter()
+    counts = 0
+    for _ in range(args.steps):
+        _, counts = fe.compress_front_discard(host_in)
+    barrier()
+    e2e_ms = maxreduce((time.perf_counter() - t0) * 1e3)
+    e2e_value = world * nbytes * args.steps / (e2e_ms / 1e3) / 1e6
+    st_e2e = fe.stats()
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    ab = algorithmic_bytes(st)
+    radix_ms = st["ms_radix"]
+    cse_ms = st["ms_cse"]
+    if radix_ms >= cse_ms:
+        k_name = "radix_onesweep_kernel"
+        k_launches = max(1, st["radix_launches"])
+        k_bytes = 24.0 * st["radix_elems"] / k_launches
+        k_ms = radix_ms / k_launches
+        note = "ms_radix covers the digit-histogram read and the host-visible sync too"
+    else:
+        k_name = "cse_rounds_kernel"
+        k_launches = max(1, st["cse_launches"])
+        k_bytes = (48.0 * st["cse_visits"] + 20.0 * st["cse_tuples"]) / k_launches
+        k_ms = cse_ms / k_launches
+        note = "one launch runs all rounds of the level loop"
+    achieved = k_bytes / (k_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": k_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "launches_per_step": k_launches,
+                "ms_per_launch": k_ms, "note": note,
+                "whole_path": {"algorithmic_bytes": ab["total"], "GBps": ab["total"] / (st["ms_total"] / 1e3) / 1e9,
+                               "frac": ab["total"] / (st["ms_total"] / 1e3) / 1e9 / peak,
+                               "stage_a_bytes": ab["stage_a"], "stage_b_bytes": ab["stage_b"]}}
+
+    gathered = batch.gather_stats(batch.RankStats(args.steps, nbytes * args.steps, 0, st["cse_tuples"], dev_ms, wall_ms),
+                                  device="cuda" if world > 1 else "cpu")
+
+    # ---- cpu baseline (rank 0, N = 1 only) ---------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        if oracle.have_ref():
+            cores = os.cpu_count() or 1
+            threads = min(8, cores)
+            sample_bytes, _ = pick_sample_bytes(gen, seed, 12.0, threads)
+            sample = synth.generate(gen, sample_bytes, seed)
+            t, r = reference_front_seconds(sample, threads)
+            cpu_baseline = {"value": sample_bytes / t / 1e6, "unit": UNIT, "cores": threads, "kind": "reference",
+                            "sample": f"first {sample_bytes} bytes of {args.workload}: unmodified bce.cpp front end via "
+                                      f"oracle/_ref (RankFile {r['seconds_rankfile']:.2f} s incl. SA-IS stand-in for "
+                                      f"libdivsufsort, CSE loop {r['seconds_encode']:.2f} s), OMP_NUM_THREADS={threads}"}
+        else:
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
+            "config": {"workload": args.workload, "generator": gen, "bytes_per_gpu": nbytes, "seed": seed,
+                       "l2": "working set (12 n bytes of keys + 8 n of SA/rank) exceeds L2; no flush",
+                       "parallelism": f"replicas x{world} (one input per GPU)"},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "stage_ms": {k: st[k] for k in ("ms_pack", "ms_radix", "ms_rerank", "ms_rekey", "ms_bwt_gather",
+                                            "ms_wavelet", "ms_cse", "ms_bwt_total", "ms_cse_total")},
+            "counters": {"sort_rounds": st["sort_rounds"], "sort_m": st["sort_m"], "sort_passes": st["sort_passes"],
+                         "visits": st["cse_visits"], "counts": st["cse_tuples"], "cse_rounds": st["cse_rounds"],
+                         "peak_frontier": st["cse_peak_frontier"]},
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+                    "d2h_bytes_per_step": int(counts) * 20 + 64, "ms_per_step": e2e_ms / args.steps,
+                    "ms_h2d": st_e2e["ms_h2d"], "ms_d2h": st_e2e["ms_d2h"]},
+            "gpu_launches": int(sum(s["gpu_launches"] for s in stats_list)),
+            "clocks": clocks,
+            "per_rank": [vars(g) for g in gathered],
+        }
+        print(json.dumps(line))
+    fe.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--bytes", type=int, default=0, help="override the input size (debugging)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload is None:
+        args.workload = "enwik-100MB" if world == 1 else "batch-128MB"
+
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+    try:
+        return run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -36,6 +36,7 @@ def main():
             ro = oracle.wavelet(Lo)
             want = oracle.cse(ro, n)
             t = time.time()
+            print(f'  .. {name}: bwt', file=sys.stderr, flush=True)
             try:
                 L, off, sa = fe.bwt(data, want_sa=True)
                 st = fe.stats()
@@ -46,6 +47,7 @@ def main():
                 msgs.append(f"[bwt rounds={st['sort_rounds']} m={st['sort_m']} P={st['sort_passes']}]")
             except Exception as e:
                 msgs.append(f"BWT EXC {e}")
+            print(f'  .. {name}: wavelet', file=sys.stderr, flush=True)
             try:
                 ranks, Cv = fe.wavelet(Lo)
                 for j in range(8):
@@ -54,6 +56,7 @@ def main():
                 if Cv != want["C"]: msgs.append(f"C {Cv} != {want['C']}")
             except Exception as e:
                 msgs.append(f"WAVELET EXC {e}")
+            print(f'  .. {name}: cse', file=sys.stderr, flush=True)
             try:
                 Cv, streams = fe.cse(Lo)
                 st = fe.stats()
@@ -66,6 +69,7 @@ def main():
             except Exception as e:
                 msgs.append(f"CSE EXC {e}")
             if prim:
+                print(f'  .. {name}: unbwt', file=sys.stderr, flush=True)
                 try:
                     out = fe.unbwt(ro, offo, n)
                     if out.tobytes() != data: msgs.append("unbwt: " + str(diff(out, np.frombuffer(data, dtype=np.uint8))))

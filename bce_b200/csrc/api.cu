@@ -9,9 +9,8 @@
 namespace bce {
 
 bool trace_on() {
-  static int on = -1;
-  if (on < 0) { const char* v = getenv("BCE_GPU_TRACE"); on = (v && *v && *v != '0') ? 1 : 0; }
-  return on == 1;
+  const char* v = getenv("BCE_GPU_TRACE");
+  return v && *v && *v != '0';
 }
 
 void set_error(Ctx* c, const char* fmt, ...) {

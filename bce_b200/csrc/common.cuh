@@ -113,13 +113,14 @@ __device__ __forceinline__ uint64_t desc_wait(const uint64_t* p, uint32_t tag, u
       atomicExch(err, 1u);
       return desc_pack(tag, kDescPrefix, 0);
     }
-    __nanosleep(32);
+    if (spins > 64) __nanosleep(20);      // poll hot at first: the usual wait is one L2 round trip
     w = desc_load(p);
   }
   return w;
 }
 
-// Serial look-back by one thread (used where 256 threads each chase their own digit).
+// Look-back by one thread (used where 256 threads each chase their own digit).  Descriptors
+// of 8 predecessors are fetched per step so that a walk of depth d costs d/8 L2 round trips.
 // Returns the exclusive prefix of `agg` over tiles [0, tile) and publishes the inclusive one.
 __device__ __forceinline__ uint32_t lookback_serial(uint64_t* desc, uint32_t stride, uint32_t tile,
                                                     uint32_t tag, uint32_t agg, uint32_t* err) {
@@ -128,11 +129,26 @@ __device__ __forceinline__ uint32_t lookback_serial(uint64_t* desc, uint32_t str
     return 0;
   }
   desc_store(desc + size_t(tile) * stride, desc_pack(tag, kDescAgg, agg));
+  constexpr int kBatch = 4;
   uint32_t excl = 0;
-  for (uint32_t t = tile; t-- > 0;) {
-    uint64_t w = desc_wait(desc + size_t(t) * stride, tag, err);
-    excl += uint32_t(w);
-    if (desc_status(w) == kDescPrefix) break;
+  uint32_t t = tile;                      // next predecessor to look at is t - 1
+  bool done = false;
+  while (!done && t > 0) {
+    uint64_t w[kBatch];
+    const uint32_t nb = t < uint32_t(kBatch) ? t : uint32_t(kBatch);
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k)
+      if (uint32_t(k) < nb) w[k] = desc_load(desc + size_t(t - 1 - k) * stride);
+#pragma unroll
+    for (int k = 0; k < kBatch; ++k) {
+      if (!done && uint32_t(k) < nb) {
+        uint64_t v = w[k];
+        if (desc_tag(v) != (tag & 0x3FFFFFFFu)) v = desc_wait(desc + size_t(t - 1 - k) * stride, tag, err);
+        excl += uint32_t(v);
+        if (desc_status(v) == kDescPrefix) done = true;
+      }
+    }
+    t -= nb;
   }
   desc_store(desc + size_t(tile) * stride, desc_pack(tag, kDescPrefix, excl + agg));
   return excl;
@@ -183,6 +199,128 @@ __device__ __forceinline__ uint32_t lookback_warp(uint64_t* desc, uint32_t tile,
     }
     excl += __reduce_add_sync(0xffffffffu, v);
     base -= 32;
+  }
+  if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescPrefix, excl + agg));
+  return excl;
+}
+
+// Warp-wide look-back for the "largest value so far" operator (values only grow along the
+// chain, so this is also "most recent non-zero").  Same protocol as lookback_warp.
+__device__ __forceinline__ uint32_t lookback_warp_max(uint64_t* desc, uint32_t tile, uint32_t first,
+                                                      uint32_t tag, uint32_t agg, uint32_t* err) {
+  const unsigned lane = lane_id();
+  if (tile == first) {
+    if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescPrefix, agg));
+    return 0;
+  }
+  // a tile that has a value of its own already knows its inclusive result
+  if (lane == 0) desc_store(desc + tile, desc_pack(tag, agg ? kDescPrefix : kDescAgg, agg));
+  uint32_t excl = 0;
+  int64_t base = int64_t(tile) - 1;
+  for (;;) {
+    int64_t t = base - lane;
+    bool inside = t >= int64_t(first);
+    uint64_t w = inside ? desc_wait(desc + t, tag, err) : desc_pack(tag, kDescPrefix, 0);
+    unsigned pm = __ballot_sync(0xffffffffu, desc_status(w) == kDescPrefix);
+    uint32_t v = uint32_t(w);
+    if (pm) {
+      unsigned stop = __ffs(pm) - 1;
+      if (lane > stop) v = 0;
+      excl = max(excl, __reduce_max_sync(0xffffffffu, v));
+      break;
+    }
+    excl = max(excl, __reduce_max_sync(0xffffffffu, v));
+    base -= 32;
+  }
+  if (lane == 0 && !agg) desc_store(desc + tile, desc_pack(tag, kDescPrefix, excl));
+  return excl;
+}
+
+// Wide-window variant of lookback_warp: every lane fetches B predecessor descriptors per
+// step (B independent loads in flight), so one step covers 32*B tiles.  A persistent kernel
+// runs gridDim tiles of the same phase at once; none of them has an inclusive prefix yet, so
+// the walk has to get past all of them -- the window is what bounds the number of serial
+// L2 round trips.
+template <int B>
+__device__ __forceinline__ uint32_t lookback_warp_wide(uint64_t* desc, uint32_t tile, uint32_t first,
+                                                       uint32_t tag, uint32_t agg, uint32_t* err) {
+  const unsigned lane = lane_id();
+  if (tile == first) {
+    if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescPrefix, agg));
+    return 0;
+  }
+  if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescAgg, agg));
+  uint32_t excl = 0;
+  int64_t base = int64_t(tile) - 1;
+  for (;;) {
+    uint64_t w[B];
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      const int64_t t = base - (k * 32 + int(lane));
+      w[k] = t >= int64_t(first) ? desc_load(desc + t) : desc_pack(tag, kDescPrefix, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      const int64_t t = base - (k * 32 + int(lane));
+      if (t >= int64_t(first) && desc_tag(w[k]) != (tag & 0x3FFFFFFFu)) w[k] = desc_wait(desc + t, tag, err);
+    }
+    bool done = false;
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      if (!done) {
+        const unsigned pm = __ballot_sync(0xffffffffu, desc_status(w[k]) == kDescPrefix);
+        uint32_t v = uint32_t(w[k]);
+        if (pm) {
+          const unsigned stop = __ffs(pm) - 1;
+          if (lane > stop) v = 0;
+          done = true;
+        }
+        excl += __reduce_add_sync(0xffffffffu, v);
+      }
+    }
+    if (done) break;
+    base -= 32 * B;
+  }
+  if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescPrefix, excl + agg));
+  return excl;
+}
+
+// The second half of lookback_warp_wide for callers that published their aggregate earlier
+// (tile != first): walk the predecessors, return the exclusive prefix, publish the inclusive one.
+template <int B>
+__device__ __forceinline__ uint32_t lookback_resolve_wide(uint64_t* desc, uint32_t tile, uint32_t first,
+                                                          uint32_t tag, uint32_t agg, uint32_t* err) {
+  const unsigned lane = lane_id();
+  uint32_t excl = 0;
+  int64_t base = int64_t(tile) - 1;
+  for (;;) {
+    uint64_t w[B];
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      const int64_t t = base - (k * 32 + int(lane));
+      w[k] = t >= int64_t(first) ? desc_load(desc + t) : desc_pack(tag, kDescPrefix, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      const int64_t t = base - (k * 32 + int(lane));
+      if (t >= int64_t(first) && desc_tag(w[k]) != (tag & 0x3FFFFFFFu)) w[k] = desc_wait(desc + t, tag, err);
+    }
+    bool done = false;
+#pragma unroll
+    for (int k = 0; k < B; ++k) {
+      if (!done) {
+        const unsigned pm = __ballot_sync(0xffffffffu, desc_status(w[k]) == kDescPrefix);
+        uint32_t v = uint32_t(w[k]);
+        if (pm) {
+          const unsigned stop = __ffs(pm) - 1;
+          if (lane > stop) v = 0;
+          done = true;
+        }
+        excl += __reduce_add_sync(0xffffffffu, v);
+      }
+    }
+    if (done) break;
+    base -= 32 * B;
   }
   if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescPrefix, excl + agg));
   return excl;

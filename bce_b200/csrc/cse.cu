@@ -20,17 +20,32 @@
 // bounded spin, so that a logic error surfaces as BCE_GPU_E_INTERNAL and never as a hung GPU.
 //
 // Algorithmic HBM bytes: 48 B per node visit + 20 B per emitted count.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 
 #include "ctx.h"
 
+namespace cg = cooperative_groups;
+
 namespace bce {
 
 constexpr int CS_THREADS = 256;
-constexpr int CS_ITEMS = 4;
-constexpr int CS_TILE = CS_THREADS * CS_ITEMS;
+// nodes per thread of the wide kernel: a template parameter (1, 2 or 4); fewer nodes per thread
+// = fewer registers = more resident CTAs to overlap the load -> gather -> scan -> look-back chain
+constexpr int CS_MAX_TILE = CS_THREADS * 4;
 
-enum : uint32_t { kCseRunning = 0, kCseDone = 1, kCseDrain = 2, kCseOverflow = 3, kCseRunaway = 4 };
+enum : uint32_t { kCseRunning = 0, kCseDone = 1, kCseDrain = 2, kCseOverflow = 3, kCseRunaway = 4,
+                  kCseGoWide = 5, kCseGoNarrow = 6 };
+
+// Narrow frontiers (the long tail: rounds ~ 8 x longest repeat, most of them with a handful of
+// nodes) run in ONE thread-block cluster of 8 CTAs, one CTA per level, frontiers in shared
+// memory, children handed to the next level's CTA through distributed shared memory, rounds
+// separated by the hardware cluster barrier instead of a grid-wide one.
+constexpr int NR_THREADS = 1024;
+constexpr int NR_CAP = 1024;                       // nodes per level held in shared memory
+constexpr uint32_t kNarrowLeave = NR_CAP / 2;      // a node has <= 2 children: the next round always fits
+constexpr uint32_t kNarrowEnter = NR_CAP / 4;      // wide -> narrow once every level is at most this
 
 struct CseDeviceState {
   uint32_t cnt[2][8][2];                 // [round parity][level][half] frontier sizes
@@ -58,12 +73,19 @@ struct CseArgs {
   uint32_t desc_tiles;
   uint32_t max_rounds;
   uint32_t round_limit;                  // no input needs more than 8 n rounds: beyond it something is broken
+  uint32_t use_narrow;                   // 1 = hand narrow frontiers to the cluster kernel
+  uint32_t dbg;                          // timing experiments only (results become wrong): 1 no look-back, 2 no gathers, 4 no flush
   CseDeviceState* st;
 };
 
 struct CseHost {
   CseArgs args;
   int grid = 0;
+  bool narrow = true;                    // which kernel runs next (the root frontier is narrow)
+  int items = 2;                         // nodes per thread of the wide kernel
+  uint32_t last_round = 0;
+  const void* wide_fn = nullptr;
+  size_t wide_smem = 0;                  // dynamic shared memory of the wide kernel
   uint32_t n = 0;
   size_t pinned_off[8] = {};
 };
@@ -132,7 +154,24 @@ __global__ void cse_reset_emitted_kernel(CseDeviceState* S) {
   if (threadIdx.x == 0 && S->status == kCseDrain) S->status = kCseRunning;
 }
 
-__global__ void __launch_bounds__(CS_THREADS, 2) cse_rounds_kernel(CseArgs a) {
+// vector load of ITEMS consecutive frontier entries; `rev` = stored back to front
+template <int ITEMS>
+__device__ __forceinline__ void load_items(const uint32_t* base, uint32_t first, bool rev, uint32_t cap, uint32_t (&out)[ITEMS]) {
+  if constexpr (ITEMS == 4) {
+    uint4 v = __ldcg(reinterpret_cast<const uint4*>(base + (rev ? cap - 4 - first : first)));
+    if (rev) { out[0] = v.w; out[1] = v.z; out[2] = v.y; out[3] = v.x; }
+    else { out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w; }
+  } else if constexpr (ITEMS == 2) {
+    uint2 v = __ldcg(reinterpret_cast<const uint2*>(base + (rev ? cap - 2 - first : first)));
+    if (rev) { out[0] = v.y; out[1] = v.x; } else { out[0] = v.x; out[1] = v.y; }
+  } else {
+    out[0] = __ldcg(base + (rev ? cap - 1 - first : first));
+  }
+}
+
+template <int CS_ITEMS>
+__global__ void __launch_bounds__(CS_THREADS, CS_ITEMS == 4 ? 2 : (CS_ITEMS == 2 ? 4 : 6)) cse_rounds_kernel(CseArgs a) {
+  constexpr int CS_TILE = CS_THREADS * CS_ITEMS;
   __shared__ uint64_t s_scan[CS_THREADS / 32];
   __shared__ uint32_t s_prefix[3];
   __shared__ uint32_t s_cnt[8][2];
@@ -144,6 +183,9 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_rounds_kernel(CseArgs a) {
   CseDeviceState* S = a.st;
   uint32_t round = vol_load(&S->round);
   uint32_t rounds_done = 0;
+  // the previous launch (either kernel) left its exit status behind; every CTA looks at the
+  // status only after the first grid barrier, so CTA 0 may clear it here
+  if (blockIdx.x == 0 && tid == 0) S->status = kCseRunning;
   const unsigned long long barrier0 = vol_load64(&S->barriers);   // barriers passed by earlier launches
 
   for (;;) {
@@ -154,7 +196,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_rounds_kernel(CseArgs a) {
     if (tid == 0) {
       uint32_t t = 0;
       unsigned long long nodes = 0;
-      uint32_t drain = 0;
+      uint32_t drain = 0, widest = 0;
       for (int l = 0; l < 8; ++l) {
         unsigned long long lvl = 0;
         for (int h = 0; h < 2; ++h) {
@@ -163,11 +205,15 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_rounds_kernel(CseArgs a) {
           lvl += s_cnt[l][h];
         }
         nodes += lvl;
+        widest = max(widest, uint32_t(min(lvl, 0xFFFFFFFFull)));
         if (s_emitted[l] + lvl > a.ecap[l]) drain = 1;   // a round emits at most one count per node
       }
       s_flags[0] = t;
-      s_flags[1] = nodes == 0 ? kCseDone : (round >= a.round_limit ? kCseRunaway : (drain ? kCseDrain : kCseRunning));
-      if (blockIdx.x == 0 && nodes && !drain && rounds_done < a.max_rounds) {
+      s_flags[1] = nodes == 0 ? kCseDone
+                 : round >= a.round_limit ? kCseRunaway
+                 : (a.use_narrow && widest <= kNarrowEnter) ? kCseGoNarrow
+                 : drain ? kCseDrain : kCseRunning;
+      if (blockIdx.x == 0 && s_flags[1] == kCseRunning && rounds_done < a.max_rounds) {
         S->visits += nodes;
         if (nodes > S->peak_frontier) S->peak_frontier = nodes;
       }
@@ -203,24 +249,13 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_rounds_kernel(CseArgs a) {
       const int nv = o0 >= count ? 0 : int(min(uint32_t(CS_ITEMS), count - o0));
       const int ln = (l + 1) & 7;
 
-      uint32_t ns[CS_ITEMS] = {0, 0, 0, 0}, na[CS_ITEMS] = {0, 0, 0, 0}, nb[CS_ITEMS] = {0, 0, 0, 0};
-      if (nv) {
-        if (hh == 0) {
-          uint4 vs = __ldcg(reinterpret_cast<const uint4*>(a.fs[cur][l] + o0));
-          uint4 va = __ldcg(reinterpret_cast<const uint4*>(a.fa[cur][l] + o0));
-          uint4 vb = __ldcg(reinterpret_cast<const uint4*>(a.fb[cur][l] + o0));
-          ns[0] = vs.x; ns[1] = vs.y; ns[2] = vs.z; ns[3] = vs.w;
-          na[0] = va.x; na[1] = va.y; na[2] = va.z; na[3] = va.w;
-          nb[0] = vb.x; nb[1] = vb.y; nb[2] = vb.z; nb[3] = vb.w;
-        } else {                       // one-half is stored back to front: ordinal o at cap-1-o
-          const uint32_t i0 = a.cap - 4 - o0;
-          uint4 vs = __ldcg(reinterpret_cast<const uint4*>(a.fs[cur][l] + i0));
-          uint4 va = __ldcg(reinterpret_cast<const uint4*>(a.fa[cur][l] + i0));
-          uint4 vb = __ldcg(reinterpret_cast<const uint4*>(a.fb[cur][l] + i0));
-          ns[0] = vs.w; ns[1] = vs.z; ns[2] = vs.y; ns[3] = vs.x;
-          na[0] = va.w; na[1] = va.z; na[2] = va.y; na[3] = va.x;
-          nb[0] = vb.w; nb[1] = vb.z; nb[2] = vb.y; nb[3] = vb.x;
-        }
+      uint32_t ns[CS_ITEMS], na[CS_ITEMS], nb[CS_ITEMS];
+#pragma unroll
+      for (int j = 0; j < CS_ITEMS; ++j) ns[j] = na[j] = nb[j] = 0;
+      if (nv) {                        // one-half is stored back to front: ordinal o at cap-1-o
+        load_items<CS_ITEMS>(a.fs[cur][l], o0, hh != 0, a.cap, ns);
+        load_items<CS_ITEMS>(a.fa[cur][l], o0, hh != 0, a.cap, na);
+        load_items<CS_ITEMS>(a.fb[cur][l], o0, hh != 0, a.cap, nb);
       }
       // three rank words per node, all independent (bce.cpp:1265, 1271, 1301)
       const uint64_t* __restrict__ R = a.ranks[l];
@@ -338,6 +373,171 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_rounds_kernel(CseArgs a) {
   }
 }
 
+}  // namespace bce
+
+#include "cse_wide.cuh"   // cse_wide_kernel<ITEMS>: the software-pipelined wide kernel (default)
+
+namespace bce {
+
+// ---------------------------------------------------------------------------------
+// narrow mode: one cluster, one CTA per level
+// ---------------------------------------------------------------------------------
+struct NarrowShared {
+  uint32_t s[2][NR_CAP], a[2][NR_CAP], b[2][NR_CAP];   // this level's frontier, double buffered
+  uint32_t cz[2], co[2];                                // zero-/one-half sizes of buffer p
+  uint32_t all_cnt[2][8];                               // every level's frontier size (all-gathered)
+  unsigned long long all_emitted[2][8];                 // every level's emission cursor (all-gathered)
+  uint64_t scan[NR_THREADS / 32];
+  uint32_t decision;
+};
+
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_narrow_kernel(CseArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ NarrowShared sh;
+  const unsigned tid = threadIdx.x;
+  const int l = int(cluster.block_rank());          // level handled by this CTA
+  const int ln = (l + 1) & 7;
+  CseDeviceState* S = a.st;
+  const uint64_t* __restrict__ R = a.ranks[l];
+
+  uint32_t round = S->round;
+  const int gpar = round & 1;
+  // frontier of this level from the wide layout (zero-half ascending, one-half from the back)
+  {
+    const uint32_t cz = S->cnt[gpar][l][0], co = S->cnt[gpar][l][1];
+    if (tid == 0) { sh.cz[0] = cz; sh.co[0] = co; }
+    for (uint32_t t = tid; t < cz + co && t < NR_CAP; t += NR_THREADS) {
+      const uint32_t idx = t < cz ? t : a.cap - 1 - (t - cz);
+      sh.s[0][t] = a.fs[gpar][l][idx];
+      sh.a[0][t] = a.fa[gpar][l][idx];
+      sh.b[0][t] = a.fb[gpar][l][idx];
+    }
+    if (tid < 8) {
+      sh.all_cnt[0][tid] = S->cnt[gpar][tid][0] + S->cnt[gpar][tid][1];
+      sh.all_emitted[0][tid] = S->emitted[gpar][tid];
+    }
+  }
+  unsigned long long cursor = S->emitted[gpar][l];
+  unsigned long long visits = 0, peak = 0;
+  int p = 0;
+  cluster.sync();                                    // nobody writes into a CTA that is still loading
+
+  uint32_t status;
+  for (;;) {
+    if (tid == 0) {
+      uint32_t total = 0, widest = 0, drain = 0;
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t cnt = sh.all_cnt[p][k];
+        total += cnt;
+        widest = max(widest, cnt);
+        if (sh.all_emitted[p][k] + cnt > a.ecap[k]) drain = 1;
+      }
+      sh.decision = total == 0 ? kCseDone
+                  : round >= a.round_limit ? kCseRunaway
+                  : widest > kNarrowLeave ? kCseGoWide
+                  : drain ? kCseDrain : kCseRunning;
+      if (sh.decision == kCseRunning) { visits += total; peak = max(peak, (unsigned long long)total); }
+    }
+    __syncthreads();
+    status = sh.decision;
+    if (status != kCseRunning) break;
+
+    const uint32_t cz = sh.cz[p], co = sh.co[p];
+    const bool live = tid < cz + co;
+    uint32_t s = 0, x0 = 0, x1 = 0;
+    if (live) { s = sh.s[p][tid]; x0 = sh.a[p][tid]; x1 = sh.b[p][tid]; }
+    uint32_t fz = 0, fo = 0, fe = 0, s0 = 0, s1 = 0, c1 = 0, z0 = 0;
+    const uint32_t x = x0 + x1;
+    if (live) {
+      const uint64_t wa = __ldg(R + (s >> 5));
+      const uint64_t wb = __ldg(R + ((s + x) >> 5));
+      const uint64_t wc = __ldg(R + ((s + x0) >> 5));
+      s1 = rank1_word(wa, s);
+      c1 = rank1_word(wb, s + x) - s1;
+      s0 = s - s1;
+      z0 = (s + x0 - rank1_word(wc, s + x0)) - s0;
+      if (c1 == 0) fz = 1;
+      else if (c1 == x) fo = 1;
+      else {
+        const uint32_t c0 = x - c1;
+        const uint32_t lo = x0 > c1 ? x0 - c1 : 0u;
+        const uint32_t hi = x0 - (c1 > x1 ? c1 - x1 : 0u);
+        fe = hi != lo;
+        const uint32_t z1 = c0 - z0, o1 = x1 - z1, o0c = c1 - o1;
+        fz = z0 && z1;
+        fo = o0c && o1;
+      }
+    }
+    const uint64_t mine = uint64_t(fz) | (uint64_t(fo) << 21) | (uint64_t(fe) << 42);
+    uint64_t tot;
+    const uint64_t excl = block_exclusive_scan<uint64_t, NR_THREADS>(mine, sh.scan, tot);
+    const uint32_t tz = uint32_t(tot) & 0x1FFFFFu, to = uint32_t(tot >> 21) & 0x1FFFFFu, te = uint32_t(tot >> 42) & 0x1FFFFFu;
+    const int q = p ^ 1;
+    // the next level's CTA receives its frontier directly in its shared memory
+    uint32_t* rs = cluster.map_shared_rank(&sh.s[q][0], ln);
+    uint32_t* ra = cluster.map_shared_rank(&sh.a[q][0], ln);
+    uint32_t* rb = cluster.map_shared_rank(&sh.b[q][0], ln);
+    if (live) {
+      uint32_t za0, za1, oa0, oa1;
+      if (c1 == 0) { za0 = x0; za1 = x1; oa0 = oa1 = 0; }
+      else if (c1 == x) { oa0 = x0; oa1 = x1; za0 = za1 = 0; }
+      else {
+        const uint32_t c0 = x - c1;
+        za0 = z0; za1 = c0 - z0;
+        oa1 = x1 - za1; oa0 = c1 - oa1;
+        if (fe) {
+          const uint32_t lo = x0 > c1 ? x0 - c1 : 0u;
+          const uint32_t hi = x0 - (c1 > x1 ? c1 - x1 : 0u);
+          const unsigned long long pe = cursor + (uint32_t(excl >> 42) & 0x1FFFFFu);
+          if (pe < a.ecap[l]) {
+            bce_tuple t;
+            t.sym = za0 - lo; t.k = hi - lo + 1; t.c1 = c0; t.c2 = x1; t.cs = x;      // bce.cpp:1302
+            a.emit[l][pe] = t;
+          }
+        }
+      }
+      if (fz) { const uint32_t at = uint32_t(excl) & 0x1FFFFFu; rs[at] = s0; ra[at] = za0; rb[at] = za1; }
+      if (fo) { const uint32_t at = tz + (uint32_t(excl >> 21) & 0x1FFFFFu); rs[at] = a.C[ln] + s1; ra[at] = oa0; rb[at] = oa1; }
+    }
+    cursor += te;
+    if (tid == 0) {
+      *cluster.map_shared_rank(&sh.cz[q], ln) = tz;
+      *cluster.map_shared_rank(&sh.co[q], ln) = to;
+    }
+    if (tid < 8) {            // all-gather: level ln's next size and this level's cursor, to every CTA
+      cluster.map_shared_rank(&sh.all_cnt[q][0], tid)[ln] = tz + to;
+      cluster.map_shared_rank(&sh.all_emitted[q][0], tid)[l] = cursor;
+    }
+    cluster.sync();
+    p = q;
+    ++round;
+  }
+
+  // hand the state back in the wide layout
+  {
+    const int opar = round & 1;
+    const uint32_t cz = sh.cz[p], co = sh.co[p];
+    for (uint32_t t = tid; t < cz + co; t += NR_THREADS) {
+      const uint32_t idx = t < cz ? t : a.cap - 1 - (t - cz);
+      a.fs[opar][l][idx] = sh.s[p][t];
+      a.fa[opar][l][idx] = sh.a[p][t];
+      a.fb[opar][l][idx] = sh.b[p][t];
+    }
+    if (tid == 0) {
+      S->cnt[opar][l][0] = cz;
+      S->cnt[opar][l][1] = co;
+      S->emitted[opar][l] = cursor;
+      if (l == 0) {
+        S->round = round;
+        S->status = status;
+        S->visits += visits;
+        if (peak > S->peak_frontier) S->peak_frontier = peak;
+      }
+    }
+  }
+  cluster.sync();     // no CTA may leave while its shared memory can still be a target
+}
+
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
@@ -365,14 +565,17 @@ int cse_begin(Ctx* c, uint32_t n) {
   const size_t cap_full = ((size_t(n) / 2 + 4) + 3) & ~size_t(3);
   size_t cap = cap_full;
   auto frontier_bytes = [](size_t cp) { return 48 * Carver::need(cp, 4); };
-  auto desc_tiles_for = [](size_t cp) { return 8 * (cp / CS_TILE + 2); };
+  const int items = int(env_size("BCE_GPU_CSE_ITEMS", 2));
+  H->items = (items == 1 || items == 4) ? items : 2;
+  const size_t tile = size_t(CS_THREADS) * H->items;
+  auto desc_tiles_for = [tile](size_t cp) { return 8 * (cp / tile + 2); };
   while (cap > 4096 && frontier_bytes(cap) > budget / 2) cap = (cap / 2 + 3) & ~size_t(3);
   const size_t desc_tiles = desc_tiles_for(cap);
   const size_t desc_bytes = Carver::need(3 * desc_tiles, 8);
   const size_t pinned_limit = env_size("BCE_GPU_PINNED_LIMIT", size_t(8) << 30);
   size_t left = budget > frontier_bytes(cap) + desc_bytes ? budget - frontier_bytes(cap) - desc_bytes : 0;
   size_t ecap = size_t(n);                                  // a level emits at most n-1 counts in total
-  const size_t per_level_min = cap + CS_TILE;               // one round must always fit
+  const size_t per_level_min = cap + CS_MAX_TILE;           // one round must always fit
   if (ecap * 8 * sizeof(bce_tuple) > left) ecap = left / (8 * sizeof(bce_tuple));
   if (ecap * 8 * sizeof(bce_tuple) > pinned_limit) ecap = pinned_limit / (8 * sizeof(bce_tuple));
   if (ecap < per_level_min) ecap = per_level_min;
@@ -396,6 +599,10 @@ int cse_begin(Ctx* c, uint32_t n) {
   a.desc_tiles = uint32_t(desc_tiles);
   a.max_rounds = 0x7FFFFFFFu;
   a.round_limit = uint32_t(std::min<uint64_t>(uint64_t(n) * 8 + 64, 0xFFFFFFF0ull));
+  a.use_narrow = env_size("BCE_GPU_NO_NARROW", 0) ? 0u : 1u;
+  a.dbg = 0;
+  H->narrow = a.use_narrow != 0;
+  H->last_round = 0;
   a.st = reinterpret_cast<CseDeviceState*>(c->small.as<char>() + kSmallCse);
   static_assert(sizeof(CseDeviceState) <= 1024, "state must fit its slot in Ctx::small");
 
@@ -404,9 +611,30 @@ int cse_begin(Ctx* c, uint32_t n) {
   c->stats.gpu_launches++;
   BCE_CUDA(c, cudaGetLastError());
 
-  if (!H->grid) {
+  {
     int per_sm = 0;
-    BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cse_rounds_kernel, CS_THREADS, 0));
+    const bool direct = env_size("BCE_GPU_CSE_DIRECT", 0) != 0 || H->items == 1;   // unpipelined variant
+    H->wide_smem = 0;
+    if (!direct && H->items == 4) {
+      H->wide_fn = (const void*)cse_wide_kernel<4>;
+      H->wide_smem = 2 * sizeof(WideStage<4>);
+      BCE_CUDA(c, cudaFuncSetAttribute(cse_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->wide_smem)));
+      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cse_wide_kernel<4>, CS_THREADS, H->wide_smem));
+    } else if (!direct) {
+      H->wide_fn = (const void*)cse_wide_kernel<2>;
+      H->wide_smem = 2 * sizeof(WideStage<2>);
+      BCE_CUDA(c, cudaFuncSetAttribute(cse_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->wide_smem)));
+      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cse_wide_kernel<2>, CS_THREADS, H->wide_smem));
+    } else if (H->items == 4) {
+      H->wide_fn = (const void*)cse_rounds_kernel<4>;
+      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cse_rounds_kernel<4>, CS_THREADS, 0));
+    } else if (H->items == 1) {
+      H->wide_fn = (const void*)cse_rounds_kernel<1>;
+      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cse_rounds_kernel<1>, CS_THREADS, 0));
+    } else {
+      H->wide_fn = (const void*)cse_rounds_kernel<2>;
+      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cse_rounds_kernel<2>, CS_THREADS, 0));
+    }
     if (per_sm < 1) { set_error(c, "cse kernel does not fit on an SM"); return BCE_GPU_E_CUDA; }
     H->grid = per_sm * c->sm_count;
   }
@@ -427,20 +655,52 @@ int cse_advance(Ctx* c, bool resident, bce_cse_batch* out) {
 
   CseDeviceState* h_state = reinterpret_cast<CseDeviceState*>(c->pinned_small.as<char>() + 40 * 1024);
   BCE_CUDA(c, cudaEventRecord(c->ev[2], st));
-  BCE_TRACE("cse launch grid=%d cap=%u ecap=%llu", H->grid, H->args.cap, H->args.ecap[0]);
-  void* kargs[] = {&H->args};
-  BCE_CUDA(c, cudaLaunchCooperativeKernel((const void*)cse_rounds_kernel, dim3(H->grid), dim3(CS_THREADS),
-                                          kargs, 0, st));
-  c->stats.gpu_launches++;
-  c->stats.cse_launches++;
-  BCE_CUDA(c, cudaMemcpyAsync(h_state, H->args.st, sizeof(CseDeviceState), cudaMemcpyDeviceToHost, st));
+  float ms = 0;
+  for (int hops = 0;; ++hops) {
+    if (hops > 100000) { set_error(c, "cse: wide/narrow ping-pong"); return BCE_GPU_E_INTERNAL; }
+    const bool was_narrow = H->narrow;
+    BCE_CUDA(c, cudaEventRecord(c->ev[0], st));
+    {
+      const uint32_t dbg_round = uint32_t(env_size("BCE_GPU_CSE_DBG_ROUND", 0));
+      H->args.max_rounds = 0x7FFFFFFFu;
+      H->args.dbg = 0;
+      if (dbg_round && !H->narrow) {
+        if (H->last_round < dbg_round) H->args.max_rounds = dbg_round - H->last_round;   // stop right before it
+        else if (H->last_round == dbg_round) { H->args.max_rounds = 1; H->args.dbg = uint32_t(env_size("BCE_GPU_CSE_DBG_FLAGS", 0)); }
+      }
+    }
+    if (H->narrow) {
+      cse_narrow_kernel<<<8, NR_THREADS, 0, st>>>(H->args);
+      BCE_CUDA(c, cudaGetLastError());
+    } else {
+      void* kargs[] = {&H->args};
+      BCE_CUDA(c, cudaLaunchCooperativeKernel(H->wide_fn, dim3(H->grid), dim3(CS_THREADS),
+                                              kargs, H->wide_smem, st));
+    }
+    c->stats.gpu_launches++;
+    c->stats.cse_launches++;
+    BCE_CUDA(c, cudaMemcpyAsync(h_state, H->args.st, sizeof(CseDeviceState), cudaMemcpyDeviceToHost, st));
+    BCE_CUDA(c, cudaEventRecord(c->ev[1], st));
+    BCE_CUDA(c, cudaStreamSynchronize(st));
+    {
+      float lms = 0;
+      BCE_CUDA(c, cudaEventElapsedTime(&lms, c->ev[0], c->ev[1]));
+      if (was_narrow) { c->stats.ms_cse_narrow += lms; c->stats.cse_rounds_narrow += h_state->round - H->last_round; }
+      BCE_TRACE("cse %s kernel: rounds %u..%u status=%u err=%u visits=%llu %.3f ms dbg=%u", was_narrow ? "narrow" : "wide",
+                H->last_round, h_state->round, h_state->status, h_state->err, h_state->visits, lms, H->args.dbg);
+      if (H->args.dbg) { set_error(c, "cse: timing experiment round done (%.3f ms)", lms); return BCE_GPU_E_INTERNAL; }
+      H->last_round = h_state->round;
+    }
+    if (h_state->err) break;
+    if (h_state->status == kCseRunning && H->args.max_rounds != 0x7FFFFFFFu) continue;   // stopped on request
+    if (h_state->status == kCseGoWide) { H->narrow = false; continue; }
+    if (h_state->status == kCseGoNarrow) { H->narrow = true; continue; }
+    break;
+  }
   BCE_CUDA(c, cudaEventRecord(c->ev[3], st));
   BCE_CUDA(c, cudaEventSynchronize(c->ev[3]));
-  float ms = 0;
   BCE_CUDA(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
   c->stats.ms_cse += ms;
-  BCE_TRACE("cse returned status=%u round=%u err=%u visits=%llu ms=%.3f", h_state->status, h_state->round,
-            h_state->err, h_state->visits, ms);
 
   if (h_state->err) {
     set_error(c, "cse: %s watchdog fired (round %u, barrier_fail %u, arrivals %llu, barriers %llu, grid %d)",

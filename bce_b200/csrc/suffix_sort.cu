@@ -162,14 +162,14 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
   uint32_t head_before = max(carry_head, lane ? prev_inc : 0u);
   uint64_t excl64 = woff + inc64 - packed;
 
-  // (3) carries across tiles: three independent chained scans
-  if (tid < 3) {
-    uint64_t* d = a.desc + size_t(tid) * a.tiles;
+  // (3) carries across tiles: three independent chained scans, one warp each
+  if (warp < 3) {
+    uint64_t* d = a.desc + size_t(warp) * a.tiles;
     uint32_t v;
-    if (tid == 0) v = lookback_serial_last(d, 1u, tile, a.tag, tile_head, a.err);
-    else if (tid == 1) v = lookback_serial(d, 1u, tile, a.tag, uint32_t(tile_sum), a.err);
-    else v = lookback_serial(d, 1u, tile, a.tag, uint32_t(tile_sum >> 32), a.err);
-    s_carry[tid] = v;
+    if (warp == 0) v = lookback_warp_max(d, tile, 0u, a.tag, tile_head, a.err);
+    else if (warp == 1) v = lookback_warp(d, tile, 0u, a.tag, uint32_t(tile_sum), a.err);
+    else v = lookback_warp(d, tile, 0u, a.tag, uint32_t(tile_sum >> 32), a.err);
+    if (lane == 0) s_carry[warp] = v;
   }
   __syncthreads();
   const uint32_t tile_head_carry = s_carry[0];

@@ -76,6 +76,8 @@ typedef struct bce_gpu_stats {
   float ms_wavelet, ms_cse;                                       /* stage B */
   float ms_unbwt_bytes, ms_unbwt_chase;                           /* inverse */
   float ms_bwt_total, ms_cse_total, ms_total;
+  float ms_cse_narrow;           /* part of ms_cse spent in the narrow-frontier (cluster) kernel */
+  uint32_t cse_rounds_narrow;    /* rounds run by it */
 } bce_gpu_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------- */

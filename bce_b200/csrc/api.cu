@@ -242,6 +242,7 @@ int bce_gpu_open(int device, bce_gpu_ctx** out) {
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+  for (int i = 0; ok && i < 256; ++i) ok = cudaEventCreate(&c->pass_ev[i]) == cudaSuccess;
   if (ok) ok = c->small.ensure(c, bce::kSmallBytes) == BCE_GPU_OK;
   if (ok) ok = c->pinned_small.ensure(c, bce::kSmallBytes) == BCE_GPU_OK;
   if (ok) ok = cudaStreamSynchronize(c->stream) == cudaSuccess;
@@ -260,6 +261,7 @@ void bce_gpu_close(bce_gpu_ctx* h) {
   c->small.release(); c->desc.release();
   c->pinned_small.release(); c->pinned_emit.release(); c->pinned_io.release();
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : c->pass_ev) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;

@@ -75,6 +75,7 @@ struct CseArgs {
   uint32_t round_limit;                  // no input needs more than 8 n rounds: beyond it something is broken
   uint32_t use_narrow;                   // 1 = hand narrow frontiers to the cluster kernel
   uint32_t dbg;                          // timing experiments only (results become wrong): 1 no look-back, 2 no gathers, 4 no flush
+  unsigned long long min_nodes, max_nodes;   // pipelined wide kernel: leave (kCseGoWide) when the frontier is outside
   CseDeviceState* st;
 };
 
@@ -86,6 +87,12 @@ struct CseHost {
   uint32_t last_round = 0;
   const void* wide_fn = nullptr;
   size_t wide_smem = 0;                  // dynamic shared memory of the wide kernel
+  // automatic mode: 1024-node tiles while the frontier is huge, 512-node tiles below
+  bool auto_items = false;
+  const void* var_fn[2] = {nullptr, nullptr};      // [0] = 2 nodes per thread, [1] = 4
+  size_t var_smem[2] = {0, 0};
+  int var_grid[2] = {0, 0};
+  unsigned long long known_nodes = 0;    // frontier size after the last launch
   uint32_t n = 0;
   size_t pinned_off[8] = {};
 };
@@ -565,9 +572,11 @@ int cse_begin(Ctx* c, uint32_t n) {
   const size_t cap_full = ((size_t(n) / 2 + 4) + 3) & ~size_t(3);
   size_t cap = cap_full;
   auto frontier_bytes = [](size_t cp) { return 48 * Carver::need(cp, 4); };
-  const int items = int(env_size("BCE_GPU_CSE_ITEMS", 2));
+  const int items = int(env_size("BCE_GPU_CSE_ITEMS", 0));
+  H->auto_items = items == 0 && env_size("BCE_GPU_CSE_DIRECT", 0) == 0;
   H->items = (items == 1 || items == 4) ? items : 2;
-  const size_t tile = size_t(CS_THREADS) * H->items;
+  H->known_nodes = 0;
+  const size_t tile = size_t(CS_THREADS);          // descriptors sized for the smallest tile of any variant
   auto desc_tiles_for = [tile](size_t cp) { return 8 * (cp / tile + 2); };
   while (cap > 4096 && frontier_bytes(cap) > budget / 2) cap = (cap / 2 + 3) & ~size_t(3);
   const size_t desc_tiles = desc_tiles_for(cap);
@@ -601,6 +610,8 @@ int cse_begin(Ctx* c, uint32_t n) {
   a.round_limit = uint32_t(std::min<uint64_t>(uint64_t(n) * 8 + 64, 0xFFFFFFF0ull));
   a.use_narrow = env_size("BCE_GPU_NO_NARROW", 0) ? 0u : 1u;
   a.dbg = 0;
+  a.min_nodes = 0;
+  a.max_nodes = ~0ull;
   H->narrow = a.use_narrow != 0;
   H->last_round = 0;
   a.st = reinterpret_cast<CseDeviceState*>(c->small.as<char>() + kSmallCse);
@@ -637,6 +648,18 @@ int cse_begin(Ctx* c, uint32_t n) {
     }
     if (per_sm < 1) { set_error(c, "cse kernel does not fit on an SM"); return BCE_GPU_E_CUDA; }
     H->grid = per_sm * c->sm_count;
+    if (H->auto_items) {
+      int p2 = 0, p4 = 0;
+      H->var_fn[0] = (const void*)cse_wide_kernel<2>; H->var_smem[0] = 2 * sizeof(WideStage<2>);
+      H->var_fn[1] = (const void*)cse_wide_kernel<4>; H->var_smem[1] = 2 * sizeof(WideStage<4>);
+      BCE_CUDA(c, cudaFuncSetAttribute(cse_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->var_smem[0])));
+      BCE_CUDA(c, cudaFuncSetAttribute(cse_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->var_smem[1])));
+      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, cse_wide_kernel<2>, CS_THREADS, H->var_smem[0]));
+      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p4, cse_wide_kernel<4>, CS_THREADS, H->var_smem[1]));
+      if (p2 < 1 || p4 < 1) { set_error(c, "cse kernel does not fit on an SM"); return BCE_GPU_E_CUDA; }
+      H->var_grid[0] = p2 * c->sm_count;
+      H->var_grid[1] = p4 * c->sm_count;
+    }
   }
   c->cse_active = true;
   c->cse_done = false;
@@ -673,9 +696,19 @@ int cse_advance(Ctx* c, bool resident, bce_cse_batch* out) {
       cse_narrow_kernel<<<8, NR_THREADS, 0, st>>>(H->args);
       BCE_CUDA(c, cudaGetLastError());
     } else {
+      const void* fn = H->wide_fn;
+      size_t smem = H->wide_smem;
+      int grid = H->grid;
+      H->args.min_nodes = 0;
+      H->args.max_nodes = ~0ull;
+      if (H->auto_items) {
+        constexpr unsigned long long kBig = 2000000, kLeaveBig = 1000000, kLeaveSmall = 3000000;
+        const int v = H->known_nodes >= kBig ? 1 : 0;
+        fn = H->var_fn[v]; smem = H->var_smem[v]; grid = H->var_grid[v];
+        if (v) H->args.min_nodes = kLeaveBig; else H->args.max_nodes = kLeaveSmall;
+      }
       void* kargs[] = {&H->args};
-      BCE_CUDA(c, cudaLaunchCooperativeKernel(H->wide_fn, dim3(H->grid), dim3(CS_THREADS),
-                                              kargs, H->wide_smem, st));
+      BCE_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(CS_THREADS), kargs, smem, st));
     }
     c->stats.gpu_launches++;
     c->stats.cse_launches++;
@@ -690,6 +723,11 @@ int cse_advance(Ctx* c, bool resident, bce_cse_batch* out) {
                 H->last_round, h_state->round, h_state->status, h_state->err, h_state->visits, lms, H->args.dbg);
       if (H->args.dbg) { set_error(c, "cse: timing experiment round done (%.3f ms)", lms); return BCE_GPU_E_INTERNAL; }
       H->last_round = h_state->round;
+    }
+    {
+      const int par = h_state->round & 1;
+      H->known_nodes = 0;
+      for (int l = 0; l < 8; ++l) H->known_nodes += h_state->cnt[par][l][0] + h_state->cnt[par][l][1];
     }
     if (h_state->err) break;
     if (h_state->status == kCseRunning && H->args.max_rounds != 0x7FFFFFFFu) continue;   // stopped on request

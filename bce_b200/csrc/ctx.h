@@ -18,6 +18,8 @@ struct Ctx : bce_gpu_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev[8] = {};
+  cudaEvent_t pass_ev[256] = {};     // start/stop pairs around individual radix passes (resolved lazily)
+  int pass_ev_n = 0;
   char err[512] = {0};
   size_t scratch_limit = 0;
 

@@ -55,6 +55,7 @@ struct RadixPass {
   uint32_t* ticket;       // tile dispenser (zero at launch)
   uint32_t tag;
   uint32_t* err;
+  uint32_t dbg;           // timing experiments only: 1 = skip the chained scan (output order wrong)
 };
 
 __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(RadixPass p) {
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(RadixPass p)
     uint32_t dstart = block_exclusive_scan<uint32_t, RS_THREADS>(sum, s_scan, tot);
     s_dstart[d] = dstart;
     uint32_t publish = (d == 255u) ? sum - (uint32_t(RS_TILE) - valid) : sum;
-    uint32_t excl = lookback_serial(p.desc + d, 256u, tile, p.tag, publish, p.err);
+    uint32_t excl = (p.dbg & 1u) ? tile * (publish ? 1u : 0u) : lookback_serial(p.desc + d, 256u, tile, p.tag, publish, p.err);
     s_goff[d] = p.base[d] + excl - dstart;     // global index = s_goff[digit] + local index
   }
   __syncthreads();
@@ -138,6 +139,8 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(RadixPass p)
     p.vout[g] = s_vals[j];
   }
 }
+
+static uint32_t g_radix_dbg = 0;
 
 int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uint32_t* valB,
                      uint32_t m, const int* shifts, int npass, uint64_t** out_k, uint32_t** out_v,
@@ -197,7 +200,11 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
     a.ticket = d_ticket + p;
     a.tag = uint32_t(next_tag(c));
     a.err = d_err;
+    a.dbg = g_radix_dbg;
+    const bool timed = c->pass_ev_n + 2 <= 256;
+    if (timed) cudaEventRecord(c->pass_ev[c->pass_ev_n], c->stream);
     radix_onesweep_kernel<<<tiles, RS_THREADS, 0, c->stream>>>(a);
+    if (timed) { cudaEventRecord(c->pass_ev[c->pass_ev_n + 1], c->stream); c->pass_ev_n += 2; }
     c->stats.gpu_launches++;
     c->stats.radix_launches++;
     c->stats.radix_elems += m;
@@ -212,4 +219,52 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
   return BCE_GPU_OK;
 }
 
+
+// ---- development aid (not part of include/bce_gpu.h): sort m pseudo-random pairs -----------
+__global__ void dbg_fill_kernel(uint64_t* k, uint32_t* v, uint32_t m) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  uint64_t z = (uint64_t(i) + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  k[i] = z ^ (z >> 31);
+  v[i] = i;
+}
+__global__ void dbg_check_kernel(const uint64_t* k, uint32_t m, uint32_t* bad) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 1 < m && k[i] > k[i + 1]) atomicAdd(bad, 1u);
+}
+
 }  // namespace bce
+
+extern "C" int bce_gpu_dbg_radix(bce_gpu_ctx* h, uint32_t m, int npass, int flags, float* ms_out, int* unsorted_out) {
+  using namespace bce;
+  Ctx* c = static_cast<Ctx*>(h);
+  cudaSetDevice(c->device);
+  size_t need = 2 * Carver::need(m, 8) + 2 * Carver::need(m, 4) + 4096;
+  BCE_TRY(c->scratch.ensure(c, need));
+  Carver cv(c->scratch.p, c->scratch.cap);
+  uint64_t* kA = cv.take<uint64_t>(m); uint64_t* kB = cv.take<uint64_t>(m);
+  uint32_t* vA = cv.take<uint32_t>(m); uint32_t* vB = cv.take<uint32_t>(m);
+  dbg_fill_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(kA, vA, m);
+  int shifts[8];
+  for (int i = 0; i < 8; ++i) shifts[i] = 8 * i;
+  g_radix_dbg = uint32_t(flags);
+  BCE_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+  uint64_t* ok; uint32_t* ov; int ran = 0;
+  int rc = radix_sort_pairs(c, kA, kB, vA, vB, m, shifts, npass, &ok, &ov, &ran);
+  g_radix_dbg = 0;
+  BCE_TRY(rc);
+  BCE_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+  uint32_t* d_bad = reinterpret_cast<uint32_t*>(c->small.as<char>() + kSmallUnbwt);
+  BCE_CUDA(c, cudaMemsetAsync(d_bad, 0, 4, c->stream));
+  dbg_check_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(ok, m, d_bad);
+  uint32_t* hb = c->pinned_small.as<uint32_t>() + 12000;
+  BCE_CUDA(c, cudaMemcpyAsync(hb, d_bad, 4, cudaMemcpyDeviceToHost, c->stream));
+  BCE_CUDA(c, cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  BCE_CUDA(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+  if (ms_out) *ms_out = ms;
+  if (unsorted_out) *unsorted_out = int(*hb);
+  return BCE_GPU_OK;
+}

@@ -282,6 +282,7 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
 
   bce_gpu_stats& S = c->stats;
   S.sort_rounds = 0;
+  c->pass_ev_n = 0;
 
   cudaEvent_t e0 = c->ev[0], e1 = c->ev[1];
   auto lap = [&](float& acc) -> int {
@@ -382,6 +383,11 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
   BCE_CUDA(c, cudaMemcpyAsync(h_small, sa, 4, cudaMemcpyDeviceToHost, st));
   BCE_TRY(lap(S.ms_bwt_gather));
   c->offset = h_small[0];
+  for (int i = 0; i + 1 < c->pass_ev_n; i += 2) {      // the stream is idle here (lap synchronised)
+    float pms = 0;
+    if (cudaEventElapsedTime(&pms, c->pass_ev[i], c->pass_ev[i + 1]) == cudaSuccess) S.ms_radix_kernel += pms;
+  }
+  c->pass_ev_n = 0;
   c->bwt_resident = true;
   if (sa_host) BCE_TRY(d2h(c, sa_host, sa, N * 4));
   return BCE_GPU_OK;

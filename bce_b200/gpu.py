@@ -56,7 +56,7 @@ class Stats(C.Structure):
         ("ms_wavelet", C.c_float), ("ms_cse", C.c_float),
         ("ms_unbwt_bytes", C.c_float), ("ms_unbwt_chase", C.c_float),
         ("ms_bwt_total", C.c_float), ("ms_cse_total", C.c_float), ("ms_total", C.c_float),
-        ("ms_cse_narrow", C.c_float), ("cse_rounds_narrow", C.c_uint32),
+        ("ms_cse_narrow", C.c_float), ("cse_rounds_narrow", C.c_uint32), ("ms_radix_kernel", C.c_float),
     ]
 
     def as_dict(self) -> dict:

@@ -78,6 +78,7 @@ typedef struct bce_gpu_stats {
   float ms_bwt_total, ms_cse_total, ms_total;
   float ms_cse_narrow;           /* part of ms_cse spent in the narrow-frontier (cluster) kernel */
   uint32_t cse_rounds_narrow;    /* rounds run by it */
+  float ms_radix_kernel;         /* sum over launches of radix_onesweep_kernel alone (event pairs) */
 } bce_gpu_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------- */

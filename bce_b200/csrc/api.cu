@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <chrono>
 #include <new>
 
 #include "ctx.h"
@@ -185,6 +186,7 @@ static int run_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
 }
 
 static int run_cse_begin(Ctx* c, uint32_t n) {
+  c->cse_emit_mode_active = int(c->emit_mode);
   cudaEvent_t a = c->ev[4], b = c->ev[5];
   BCE_CUDA(c, cudaEventRecord(a, c->stream));
   BCE_TRY(wavelet_build(c, n));
@@ -338,9 +340,17 @@ int bce_gpu_cse_begin(bce_gpu_ctx* h, const uint8_t* L, uint32_t n, uint32_t C_o
   bce::begin_call(c);
   BCE_TRY(bce::check_n(c, n));
   if (L) bce::reset_stats(c, n);
+  c->cse_resident = false;
   BCE_TRY(load_bwt(c, L, n));
   BCE_TRY(bce::run_cse_begin(c, n));
   if (C_out) for (int i = 0; i < 8; ++i) C_out[i] = c->C[i];
+  return BCE_GPU_OK;
+}
+
+static int next_words(Ctx* c, bce::CseWordBatch* wb) {
+  const auto t0 = std::chrono::steady_clock::now();
+  BCE_TRY(bce::cse_advance(c, false, wb));
+  c->stats.ms_cse_total += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return BCE_GPU_OK;
 }
 
@@ -348,14 +358,53 @@ int bce_gpu_cse_next(bce_gpu_ctx* h, bce_cse_batch* out) {
   if (!h || !out) return BCE_GPU_E_ARG;
   Ctx* c = static_cast<Ctx*>(h);
   bce::begin_call(c);
-  cudaEvent_t a = c->ev[4], b = c->ev[5];
-  BCE_CUDA(c, cudaEventRecord(a, c->stream));
-  BCE_TRY(bce::cse_advance(c, false, out));
-  BCE_CUDA(c, cudaEventRecord(b, c->stream));
-  BCE_CUDA(c, cudaEventSynchronize(b));
-  float ms = 0;
-  BCE_CUDA(c, cudaEventElapsedTime(&ms, a, b));
-  c->stats.ms_cse_total += ms;
+  if (c->cse_active && c->cse_emit_mode_active != BCE_EMIT_RAW) {
+    bce::set_error(c, "cse_next: the run emits packed words, use bce_gpu_cse_next_words");
+    return BCE_GPU_E_STATE;
+  }
+  bce::CseWordBatch wb;
+  BCE_TRY(next_words(c, &wb));
+  for (int i = 0; i < 8; ++i) {
+    out->tuples[i] = reinterpret_cast<const bce_tuple*>(wb.words[i]);
+    out->count[i] = wb.count[i] / 5;
+  }
+  out->done = wb.done;
+  return BCE_GPU_OK;
+}
+
+int bce_gpu_cse_next_words(bce_gpu_ctx* h, bce_cse_words* out) {
+  if (!h || !out) return BCE_GPU_E_ARG;
+  Ctx* c = static_cast<Ctx*>(h);
+  bce::begin_call(c);
+  bce::CseWordBatch wb;
+  BCE_TRY(next_words(c, &wb));
+  for (int i = 0; i < 8; ++i) { out->words[i] = wb.words[i]; out->count[i] = wb.count[i]; }
+  out->done = wb.done;
+  return BCE_GPU_OK;
+}
+
+int bce_gpu_set_emit_mode(bce_gpu_ctx* h, int mode, const uint8_t* cfg288) {
+  if (!h || mode < BCE_EMIT_RAW || mode > BCE_EMIT_SCAN) return BCE_GPU_E_ARG;
+  Ctx* c = static_cast<Ctx*>(h);
+  static const uint8_t kDefault[8][32] = {                              // bce.cpp:713-724, rows 0..7
+    {0,0,5,5,5,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,0},
+    {0,0,5,5,5,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,0},
+    {0,0,5,5,5,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,3,3,3,3,0},
+    {0,0,5,5,5,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,3,3,3,3,3,3,3,3,3,0},
+    {0,0,5,5,4,4,4,4,4,4,4,4,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,0},
+    {0,0,5,5,4,4,4,4,4,4,4,4,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,0},
+    {0,0,5,4,4,4,4,4,4,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,0},
+    {0,0,4,4,4,4,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,3,2,2,2,2,2,2,0}};
+  c->emit_mode = uint32_t(mode);
+  if (cfg288) {
+    for (int i = 0; i < 8; ++i)
+      for (int k = 0; k < 32; ++k) {
+        if (cfg288[i * 32 + k] > 5) { bce::set_error(c, "config: context bits %u > 5", cfg288[i * 32 + k]); return BCE_GPU_E_ARG; }
+        c->emit_cfg[i][k] = cfg288[i * 32 + k];
+      }
+  } else {
+    memcpy(c->emit_cfg, kDefault, sizeof kDefault);
+  }
   return BCE_GPU_OK;
 }
 
@@ -367,6 +416,7 @@ int bce_gpu_compress_front(bce_gpu_ctx* h, const uint8_t* T, uint32_t n, uint32_
   BCE_TRY(bce::check_n(c, n));
   bce::reset_stats(c, n);
   c->cse_active = false;
+  c->cse_resident = false;
   BCE_TRY(bce::upload_text(c, T, n));
   BCE_TRY(bce::run_bwt(c, n, nullptr));
   BCE_TRY(bce::run_cse_begin(c, n));
@@ -395,6 +445,7 @@ int bce_gpu_front_resident(bce_gpu_ctx* h, uint32_t* offset_out, uint64_t* tuple
   bce::reset_stats(c, n);
   c->stats.ms_h2d = h2d_ms;
   c->cse_active = false;
+  c->cse_resident = true;
   BCE_TRY(bce::run_bwt(c, n, nullptr));
   BCE_TRY(bce::run_cse_begin(c, n));
   while (!c->cse_done) {
@@ -409,7 +460,7 @@ int bce_gpu_front_resident(bce_gpu_ctx* h, uint32_t* offset_out, uint64_t* tuple
   }
   c->stats.ms_total = c->stats.ms_bwt_total + c->stats.ms_cse_total;
   if (offset_out) *offset_out = c->offset;
-  if (tuples_out) *tuples_out = c->stats.cse_tuples;
+  if (tuples_out) *tuples_out = c->emit_mode == BCE_EMIT_RAW ? c->stats.cse_tuples : c->stats.cse_words;
   return BCE_GPU_OK;
 }
 

@@ -7,17 +7,23 @@
 // (i+1)%8.  Nodes are independent; what the archive depends on is only the ORDER of the
 // emitted counts per stream: ascending round, ascending position.
 //
-// Device design: one persistent cooperative kernel runs many rounds.  Per round all 8
-// levels are processed together; the frontier of a level is a flat array sorted by position
-// (zero-half from the front, one-half from the back of one buffer).  A tile of 1024 nodes:
-//   load nodes (128-bit), 12 independent rank-word gathers per thread, derive
-//   (emit?, zero-child?, one-child?) -> block scan of the three counts -> chained scan over
-//   the tiles of the level (warp-wide decoupled look-back, three carried values)
-//   -> write counts, zero-children and one-children at their exact ordered positions.
-// So the stable partition into the next level's halves and the emission order fall out of
-// prefix sums; no atomics decide any position.  A grid-wide barrier separates rounds: a
-// monotonically increasing arrival counter (all CTAs are co-resident: cooperative launch) with a
-// bounded spin, so that a logic error surfaces as BCE_GPU_E_INTERNAL and never as a hung GPU.
+// Device design.  The frontier of a level is a flat structure-of-arrays list sorted by position
+// (zero-half from the front, one-half from the back of one buffer).  Per round and level three
+// prefix sums -- zero-children, one-children, emitted words -- fix every output position, so
+// the stable partition into the next level's halves and the emission order need no atomics.
+//   wide frontiers    cse_wide_kernel (cse_wide.cuh): persistent cooperative kernel, all SMs,
+//                     software pipelined tiles, grid barrier between rounds
+//   narrow frontiers  cse_narrow_kernel (below): ONE cluster of 8 CTAs, one per level, frontiers
+//                     in shared memory, children handed over through distributed shared memory,
+//                     hardware cluster barrier between rounds
+// The host alternates between the two on the kernels' request and drains the emission buffers.
+//
+// Emission is word based.  Raw mode writes the five arguments of set() (20 B, bce_tuple);
+// the packed modes write what the host coder actually consumes (4 B, 8 B when k > 31):
+//   coder  [esc:1|nb:5 @20|ctx:10 @10|k:5 @5|sym:5]   ctx = get_context index, bce.cpp:671-677,
+//          for the stream's configured context bits; esc: k > 31 was halved nb times
+//          (bce.cpp:507-510), a second word carries the nb low bits of the symbol
+//   scan   [esc:1|nb:5 @26|q2:8 @18|q1:8 @10|k:5 @5|sym:5]   ScanCoder::set, bce.cpp:737-744
 //
 // Algorithmic HBM bytes: 48 B per node visit + 20 B per emitted count.
 #include <cooperative_groups.h>
@@ -31,17 +37,12 @@ namespace cg = cooperative_groups;
 namespace bce {
 
 constexpr int CS_THREADS = 256;
-// nodes per thread of the wide kernel: a template parameter (1, 2 or 4); fewer nodes per thread
-// = fewer registers = more resident CTAs to overlap the load -> gather -> scan -> look-back chain
 constexpr int CS_MAX_TILE = CS_THREADS * 4;
 
 enum : uint32_t { kCseRunning = 0, kCseDone = 1, kCseDrain = 2, kCseOverflow = 3, kCseRunaway = 4,
                   kCseGoWide = 5, kCseGoNarrow = 6 };
+enum : uint32_t { kEmitRaw = 0, kEmitCoder = 1, kEmitScan = 2 };
 
-// Narrow frontiers (the long tail: rounds ~ 8 x longest repeat, most of them with a handful of
-// nodes) run in ONE thread-block cluster of 8 CTAs, one CTA per level, frontiers in shared
-// memory, children handed to the next level's CTA through distributed shared memory, rounds
-// separated by the hardware cluster barrier instead of a grid-wide one.
 constexpr int NR_THREADS = 1024;
 constexpr int NR_CAP = 1024;                       // nodes per level held in shared memory
 constexpr uint32_t kNarrowLeave = NR_CAP / 2;      // a node has <= 2 children: the next round always fits
@@ -49,15 +50,15 @@ constexpr uint32_t kNarrowEnter = NR_CAP / 4;      // wide -> narrow once every 
 
 struct CseDeviceState {
   uint32_t cnt[2][8][2];                 // [round parity][level][half] frontier sizes
-  unsigned long long emitted[2][8];      // [round parity][level] counts in the emission buffer
+  unsigned long long emitted[2][8];      // [round parity][level] words in the emission buffer
   unsigned long long visits;
   unsigned long long peak_frontier;
   uint32_t round;
   uint32_t status;
-  uint32_t err;                          // chained-scan watchdog
+  uint32_t err;                          // 1 = chained-scan watchdog, 2 = grid-barrier watchdog
   uint32_t barrier_fail;                 // round at which the grid barrier timed out (+1), 0 = never
   unsigned long long arrivals;           // grid barrier: total CTA arrivals since cse_begin
-  unsigned long long barriers;           // grid barriers completed since cse_begin (host-maintained between launches)
+  unsigned long long barriers;           // grid barriers completed since cse_begin
 };
 
 struct CseArgs {
@@ -67,34 +68,18 @@ struct CseArgs {
   uint32_t* fa[2][8];                    //   x0
   uint32_t* fb[2][8];                    //   x1
   uint32_t cap;                          // nodes per frontier buffer, multiple of 4
-  bce_tuple* emit[8];
-  unsigned long long ecap[8];
+  uint32_t* emit[8];                     // emission buffers (words)
+  unsigned long long ecap[8];            // their capacity in words
   uint64_t* desc;                        // 3 x desc_tiles
   uint32_t desc_tiles;
   uint32_t max_rounds;
   uint32_t round_limit;                  // no input needs more than 8 n rounds: beyond it something is broken
   uint32_t use_narrow;                   // 1 = hand narrow frontiers to the cluster kernel
   uint32_t dbg;                          // timing experiments only (results become wrong): 1 no look-back, 2 no gathers, 4 no flush
-  unsigned long long min_nodes, max_nodes;   // pipelined wide kernel: leave (kCseGoWide) when the frontier is outside
+  uint32_t emit_mode;                    // kEmitRaw / kEmitCoder / kEmitScan
+  unsigned long long min_nodes, max_nodes;   // wide kernel: leave (kCseGoWide) when the frontier is outside
+  uint8_t cfgbits[8][32];                // kEmitCoder: context bits per (stream, k), bce.cpp:713-724
   CseDeviceState* st;
-};
-
-struct CseHost {
-  CseArgs args;
-  int grid = 0;
-  bool narrow = true;                    // which kernel runs next (the root frontier is narrow)
-  int items = 2;                         // nodes per thread of the wide kernel
-  uint32_t last_round = 0;
-  const void* wide_fn = nullptr;
-  size_t wide_smem = 0;                  // dynamic shared memory of the wide kernel
-  // automatic mode: 1024-node tiles while the frontier is huge, 512-node tiles below
-  bool auto_items = false;
-  const void* var_fn[2] = {nullptr, nullptr};      // [0] = 2 nodes per thread, [1] = 4
-  size_t var_smem[2] = {0, 0};
-  int var_grid[2] = {0, 0};
-  unsigned long long known_nodes = 0;    // frontier size after the last launch
-  uint32_t n = 0;
-  size_t pinned_off[8] = {};
 };
 
 __device__ __forceinline__ uint32_t rank1_word(uint64_t w, uint32_t pos) {      // Rank::get<1>, bce.cpp:147-151
@@ -111,10 +96,41 @@ __device__ __forceinline__ unsigned long long vol_load64(const unsigned long lon
   return v;
 }
 
+// One emitted count -> words.  Returns the number of words (5 raw, 1 or 2 packed); e0..e2 hold
+// them (raw: sym, k, c1 -- the caller appends c2 = x1 and cs = x).
+__device__ __forceinline__ uint32_t count_words(const CseArgs& a, int level, uint32_t sym, uint32_t k,
+                                                uint32_t c1, uint32_t c2, uint32_t cs,
+                                                uint32_t& e0, uint32_t& e1, uint32_t& e2) {
+  if (a.emit_mode == kEmitRaw) { e0 = sym; e1 = k; e2 = c1; return 5u; }
+  uint32_t nb = 0, s = sym;
+  if (a.emit_mode == kEmitCoder) {
+    while (k > 31u) { k = (k + (~s & 1u)) >> 1; s >>= 1; ++nb; }                 // bce.cpp:507-510
+    const uint32_t b = a.cfgbits[level][k];
+    const uint32_t ctx = (((c1 << b) / cs) << b) | ((c2 << b) / cs);            // bce.cpp:674 (uint32 wrap)
+    const uint32_t w = (ctx << 10) | (k << 5) | s;
+    e2 = 0;
+    if (nb == 0) { e0 = w; e1 = 0; return 1u; }
+    e0 = 0x80000000u | (nb << 20) | w;
+    e1 = sym & ((1u << nb) - 1u);
+    return 2u;
+  }
+  while (k > 31u) { k = (k >> 1) + (~s & 1u); s >>= 1; ++nb; }                   // bce.cpp:738-741
+  const uint32_t q1 = (c1 << 8) / cs, q2 = (c2 << 8) / cs;                        // bce.cpp:743
+  e0 = (nb ? 0x80000000u | (nb << 26) : 0u) | (q2 << 18) | (q1 << 10) | (k << 5) | s;
+  e1 = e2 = 0;
+  return 1u;
+}
+__device__ __forceinline__ void put_words(uint32_t* dst, uint32_t nw, uint32_t e0, uint32_t e1, uint32_t e2,
+                                          uint32_t x1, uint32_t x) {
+  dst[0] = e0;
+  if (nw == 5u) { dst[1] = e1; dst[2] = e2; dst[3] = x1; dst[4] = x; }
+  else if (nw == 2u) dst[1] = e1;
+}
+__device__ __forceinline__ uint32_t max_words(const CseArgs& a) { return a.emit_mode == kEmitRaw ? 5u : 2u; }
+
 // Grid-wide barrier.  Every CTA adds one arrival; barrier number b (0-based, counted since
 // cse_begin) is passed when the counter reaches (b + 1) * gridDim.x.  The counter only grows,
-// so there is no reset race.  Returns false (and records the failure) if the others do not
-// arrive within the spin budget.
+// so there is no reset race.  The spin is bounded: a logic error becomes BCE_GPU_E_INTERNAL.
 __device__ __forceinline__ bool grid_barrier(CseDeviceState* S, unsigned long long index, uint32_t round) {
   __syncthreads();
   bool ok = true;
@@ -130,7 +146,7 @@ __device__ __forceinline__ bool grid_barrier(CseDeviceState* S, unsigned long lo
         ok = false;
         break;
       }
-      __nanosleep(20);
+      if (spins > 32) __nanosleep(20);
     }
     __threadfence();
   }
@@ -176,213 +192,9 @@ __device__ __forceinline__ void load_items(const uint32_t* base, uint32_t first,
   }
 }
 
-template <int CS_ITEMS>
-__global__ void __launch_bounds__(CS_THREADS, CS_ITEMS == 4 ? 2 : (CS_ITEMS == 2 ? 4 : 6)) cse_rounds_kernel(CseArgs a) {
-  constexpr int CS_TILE = CS_THREADS * CS_ITEMS;
-  __shared__ uint64_t s_scan[CS_THREADS / 32];
-  __shared__ uint32_t s_prefix[3];
-  __shared__ uint32_t s_cnt[8][2];
-  __shared__ uint32_t s_tstart[8][2];       // first global tile of (level, half)
-  __shared__ unsigned long long s_emitted[8];
-  __shared__ uint32_t s_flags[2];
-
-  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  CseDeviceState* S = a.st;
-  uint32_t round = vol_load(&S->round);
-  uint32_t rounds_done = 0;
-  // the previous launch (either kernel) left its exit status behind; every CTA looks at the
-  // status only after the first grid barrier, so CTA 0 may clear it here
-  if (blockIdx.x == 0 && tid == 0) S->status = kCseRunning;
-  const unsigned long long barrier0 = vol_load64(&S->barriers);   // barriers passed by earlier launches
-
-  for (;;) {
-    const int cur = round & 1, nxt = cur ^ 1;
-    if (tid < 16) s_cnt[tid >> 1][tid & 1] = vol_load(&S->cnt[cur][tid >> 1][tid & 1]);
-    if (tid >= 32 && tid < 40) s_emitted[tid - 32] = vol_load64(&S->emitted[cur][tid - 32]);
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t t = 0;
-      unsigned long long nodes = 0;
-      uint32_t drain = 0, widest = 0;
-      for (int l = 0; l < 8; ++l) {
-        unsigned long long lvl = 0;
-        for (int h = 0; h < 2; ++h) {
-          s_tstart[l][h] = t;
-          t += (s_cnt[l][h] + CS_TILE - 1) / CS_TILE;
-          lvl += s_cnt[l][h];
-        }
-        nodes += lvl;
-        widest = max(widest, uint32_t(min(lvl, 0xFFFFFFFFull)));
-        if (s_emitted[l] + lvl > a.ecap[l]) drain = 1;   // a round emits at most one count per node
-      }
-      s_flags[0] = t;
-      s_flags[1] = nodes == 0 ? kCseDone
-                 : round >= a.round_limit ? kCseRunaway
-                 : (a.use_narrow && widest <= kNarrowEnter) ? kCseGoNarrow
-                 : drain ? kCseDrain : kCseRunning;
-      if (blockIdx.x == 0 && s_flags[1] == kCseRunning && rounds_done < a.max_rounds) {
-        S->visits += nodes;
-        if (nodes > S->peak_frontier) S->peak_frontier = nodes;
-      }
-    }
-    __syncthreads();
-    const uint32_t total_tiles = s_flags[0];
-    const uint32_t decision = s_flags[1];
-    if (decision != kCseRunning || rounds_done >= a.max_rounds) {
-      if (blockIdx.x == 0 && tid == 0) { S->status = decision; S->round = round; S->barriers = barrier0 + rounds_done; }
-      break;
-    }
-    // levels without nodes hand an empty frontier (and their emission cursor) to the next round
-    if (blockIdx.x == 0 && tid < 8) {
-      const int l = tid;
-      if (s_cnt[l][0] + s_cnt[l][1] == 0) {
-        S->cnt[nxt][(l + 1) & 7][0] = 0;
-        S->cnt[nxt][(l + 1) & 7][1] = 0;
-        S->emitted[nxt][l] = s_emitted[l];
-      }
-    }
-    const uint32_t tag = round + 1;
-
-    for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      // which (level, half) does this tile belong to?
-      int l = 0, hh = 0;
-#pragma unroll
-      for (int k = 1; k < 16; ++k)
-        if (tile >= s_tstart[k >> 1][k & 1]) { l = k >> 1; hh = k & 1; }
-      // (s_tstart is non-decreasing; an empty (level, half) shares its start with the next one,
-      //  the loop keeps the last match, which is the non-empty owner)
-      const uint32_t count = s_cnt[l][hh];
-      const uint32_t o0 = (tile - s_tstart[l][hh]) * CS_TILE + tid * CS_ITEMS;
-      const int nv = o0 >= count ? 0 : int(min(uint32_t(CS_ITEMS), count - o0));
-      const int ln = (l + 1) & 7;
-
-      uint32_t ns[CS_ITEMS], na[CS_ITEMS], nb[CS_ITEMS];
-#pragma unroll
-      for (int j = 0; j < CS_ITEMS; ++j) ns[j] = na[j] = nb[j] = 0;
-      if (nv) {                        // one-half is stored back to front: ordinal o at cap-1-o
-        load_items<CS_ITEMS>(a.fs[cur][l], o0, hh != 0, a.cap, ns);
-        load_items<CS_ITEMS>(a.fa[cur][l], o0, hh != 0, a.cap, na);
-        load_items<CS_ITEMS>(a.fb[cur][l], o0, hh != 0, a.cap, nb);
-      }
-      // three rank words per node, all independent (bce.cpp:1265, 1271, 1301)
-      const uint64_t* __restrict__ R = a.ranks[l];
-      uint64_t wa[CS_ITEMS], wb[CS_ITEMS], wc[CS_ITEMS];
-#pragma unroll
-      for (int j = 0; j < CS_ITEMS; ++j) {
-        if (j < nv) {
-          wa[j] = __ldg(R + (ns[j] >> 5));
-          wb[j] = __ldg(R + ((ns[j] + na[j] + nb[j]) >> 5));
-          wc[j] = __ldg(R + ((ns[j] + na[j]) >> 5));
-        } else { wa[j] = wb[j] = wc[j] = 0; }
-      }
-      uint32_t s0v[CS_ITEMS], s1v[CS_ITEMS], n1x[CS_ITEMS], n0x0[CS_ITEMS];
-      uint32_t fz = 0, fo = 0, fe = 0;           // bit j: node j has zero-child / one-child / emits
-#pragma unroll
-      for (int j = 0; j < CS_ITEMS; ++j) {
-        if (j < nv) {
-          const uint32_t s = ns[j], x0 = na[j], x1 = nb[j], x = x0 + x1;
-          const uint32_t s1 = rank1_word(wa[j], s);
-          const uint32_t c1 = rank1_word(wb[j], s + x) - s1;         // _1x
-          const uint32_t s0 = s - s1;
-          const uint32_t z0 = (s + x0 - rank1_word(wc[j], s + x0)) - s0;   // _0x0 by rank (:1301)
-          s0v[j] = s0; s1v[j] = s1; n1x[j] = c1; n0x0[j] = z0;
-          if (c1 == 0) fz |= 1u << j;                                 // :1274
-          else if (c1 == x) fo |= 1u << j;                            // :1282
-          else {
-            const uint32_t c0 = x - c1;
-            const uint32_t lo = x0 > c1 ? x0 - c1 : 0u;               // :1290-1294
-            const uint32_t hi = x0 - (c1 > x1 ? c1 - x1 : 0u);
-            if (hi != lo) fe |= 1u << j;                              // :1299
-            const uint32_t z1 = c0 - z0;                              // _0x1
-            const uint32_t o1 = x1 - z1;                              // _1x1
-            const uint32_t o0c = c1 - o1;                             // _1x0
-            if (z0 && z1) fz |= 1u << j;                              // :1338
-            if (o0c && o1) fo |= 1u << j;                             // :1345
-          }
-        }
-      }
-      // ordered positions by prefix sums: (zero-children | one-children | counts) in 3 x 21 bits
-      const uint64_t mine = uint64_t(__popc(fz)) | (uint64_t(__popc(fo)) << 21) | (uint64_t(__popc(fe)) << 42);
-      uint64_t tile_tot;
-      const uint64_t excl = block_exclusive_scan<uint64_t, CS_THREADS>(mine, s_scan, tile_tot);
-      const uint32_t first = s_tstart[l][0];
-      if (warp < 3) {
-        const uint32_t agg = uint32_t(tile_tot >> (21 * warp)) & 0x1FFFFFu;
-        const uint32_t pre = lookback_warp(a.desc + size_t(warp) * a.desc_tiles, tile, first, tag, agg, &S->err);
-        if (lane == 0) s_prefix[warp] = pre;
-      }
-      __syncthreads();
-      uint32_t pz = s_prefix[0] + (uint32_t(excl) & 0x1FFFFFu);
-      uint32_t po = s_prefix[1] + (uint32_t(excl >> 21) & 0x1FFFFFu);
-      unsigned long long pe = s_emitted[l] + s_prefix[2] + (uint32_t(excl >> 42) & 0x1FFFFFu);
-
-      uint32_t* __restrict__ zs = a.fs[nxt][ln];
-      uint32_t* __restrict__ za = a.fa[nxt][ln];
-      uint32_t* __restrict__ zb = a.fb[nxt][ln];
-      bce_tuple* __restrict__ em = a.emit[l];
-      const uint32_t one_base = a.C[ln];
-#pragma unroll
-      for (int j = 0; j < CS_ITEMS; ++j) {
-        if (j < nv) {
-          const uint32_t x0 = na[j], x1 = nb[j], x = x0 + x1, c1 = n1x[j];
-          uint32_t za0, za1, oa0, oa1;                                 // child payloads
-          if (c1 == 0) { za0 = x0; za1 = x1; oa0 = oa1 = 0; }
-          else if (c1 == x) { oa0 = x0; oa1 = x1; za0 = za1 = 0; }
-          else {
-            const uint32_t c0 = x - c1;
-            za0 = n0x0[j]; za1 = c0 - za0;
-            oa1 = x1 - za1; oa0 = c1 - oa1;
-            if (fe >> j & 1u) {
-              const uint32_t lo = x0 > c1 ? x0 - c1 : 0u;
-              const uint32_t hi = x0 - (c1 > x1 ? c1 - x1 : 0u);
-              if (pe < a.ecap[l]) {
-                bce_tuple t;
-                t.sym = za0 - lo; t.k = hi - lo + 1; t.c1 = c0; t.c2 = x1; t.cs = x;   // :1302
-                em[pe] = t;
-              }
-              ++pe;
-            }
-          }
-          if (fz >> j & 1u) {
-            if (pz < a.cap) { zs[pz] = s0v[j]; za[pz] = za0; zb[pz] = za1; }
-            ++pz;
-          }
-          if (fo >> j & 1u) {
-            if (po < a.cap) {
-              const uint32_t at = a.cap - 1 - po;
-              zs[at] = one_base + s1v[j]; za[at] = oa0; zb[at] = oa1;
-            }
-            ++po;
-          }
-        }
-      }
-      // the last tile of a level knows the level's totals: publish the next frontier sizes
-      const uint32_t level_tiles = (s_cnt[l][0] + CS_TILE - 1) / CS_TILE + (s_cnt[l][1] + CS_TILE - 1) / CS_TILE;
-      if (tile == first + level_tiles - 1 && tid == 0) {
-        const uint32_t tz = s_prefix[0] + (uint32_t(tile_tot) & 0x1FFFFFu);
-        const uint32_t to = s_prefix[1] + (uint32_t(tile_tot >> 21) & 0x1FFFFFu);
-        const uint32_t te = s_prefix[2] + (uint32_t(tile_tot >> 42) & 0x1FFFFFu);
-        S->cnt[nxt][ln][0] = tz;
-        S->cnt[nxt][ln][1] = to;
-        S->emitted[nxt][l] = s_emitted[l] + te;
-        if (uint64_t(tz) + to > a.cap) atomicExch(&S->status, uint32_t(kCseOverflow));
-      }
-      __syncthreads();        // s_prefix / s_scan are reused by the next tile
-    }
-
-    grid_barrier(S, barrier0 + rounds_done, round);
-    ++round;
-    ++rounds_done;
-    if (vol_load(&S->status) != kCseRunning || vol_load(&S->err) != 0) {
-      if (blockIdx.x == 0 && tid == 0) { S->round = round; S->barriers = barrier0 + rounds_done; }
-      break;
-    }
-  }
-}
-
 }  // namespace bce
 
-#include "cse_wide.cuh"   // cse_wide_kernel<ITEMS>: the software-pipelined wide kernel (default)
+#include "cse_wide.cuh"   // cse_wide_kernel<ITEMS>: the software-pipelined wide kernel
 
 namespace bce {
 
@@ -406,6 +218,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_n
   const int ln = (l + 1) & 7;
   CseDeviceState* S = a.st;
   const uint64_t* __restrict__ R = a.ranks[l];
+  const uint32_t maxw = max_words(a);
 
   uint32_t round = S->round;
   const int gpar = round & 1;
@@ -437,7 +250,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_n
         const uint32_t cnt = sh.all_cnt[p][k];
         total += cnt;
         widest = max(widest, cnt);
-        if (sh.all_emitted[p][k] + cnt > a.ecap[k]) drain = 1;
+        if (sh.all_emitted[p][k] + (unsigned long long)cnt * maxw > a.ecap[k]) drain = 1;
       }
       sh.decision = total == 0 ? kCseDone
                   : round >= a.round_limit ? kCseRunaway
@@ -453,7 +266,8 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_n
     const bool live = tid < cz + co;
     uint32_t s = 0, x0 = 0, x1 = 0;
     if (live) { s = sh.s[p][tid]; x0 = sh.a[p][tid]; x1 = sh.b[p][tid]; }
-    uint32_t fz = 0, fo = 0, fe = 0, s0 = 0, s1 = 0, c1 = 0, z0 = 0;
+    uint32_t fz = 0, fo = 0, nw = 0, s0 = 0, s1 = 0, c1 = 0, z0 = 0, e0 = 0, e1 = 0, e2 = 0;
+    uint32_t za0 = 0, za1 = 0, oa0 = 0, oa1 = 0;
     const uint32_t x = x0 + x1;
     if (live) {
       const uint64_t wa = __ldg(R + (s >> 5));
@@ -463,19 +277,19 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_n
       c1 = rank1_word(wb, s + x) - s1;
       s0 = s - s1;
       z0 = (s + x0 - rank1_word(wc, s + x0)) - s0;
-      if (c1 == 0) fz = 1;
-      else if (c1 == x) fo = 1;
+      if (c1 == 0) { fz = 1; za0 = x0; za1 = x1; }
+      else if (c1 == x) { fo = 1; oa0 = x0; oa1 = x1; }
       else {
         const uint32_t c0 = x - c1;
         const uint32_t lo = x0 > c1 ? x0 - c1 : 0u;
         const uint32_t hi = x0 - (c1 > x1 ? c1 - x1 : 0u);
-        fe = hi != lo;
         const uint32_t z1 = c0 - z0, o1 = x1 - z1, o0c = c1 - o1;
-        fz = z0 && z1;
-        fo = o0c && o1;
+        if (hi != lo) nw = count_words(a, l, z0 - lo, hi - lo + 1, c0, x1, x, e0, e1, e2);   // bce.cpp:1302
+        if (z0 && z1) { fz = 1; za0 = z0; za1 = z1; }
+        if (o0c && o1) { fo = 1; oa0 = o0c; oa1 = o1; }
       }
     }
-    const uint64_t mine = uint64_t(fz) | (uint64_t(fo) << 21) | (uint64_t(fe) << 42);
+    const uint64_t mine = uint64_t(fz) | (uint64_t(fo) << 21) | (uint64_t(nw) << 42);
     uint64_t tot;
     const uint64_t excl = block_exclusive_scan<uint64_t, NR_THREADS>(mine, sh.scan, tot);
     const uint32_t tz = uint32_t(tot) & 0x1FFFFFu, to = uint32_t(tot >> 21) & 0x1FFFFFu, te = uint32_t(tot >> 42) & 0x1FFFFFu;
@@ -485,23 +299,9 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_n
     uint32_t* ra = cluster.map_shared_rank(&sh.a[q][0], ln);
     uint32_t* rb = cluster.map_shared_rank(&sh.b[q][0], ln);
     if (live) {
-      uint32_t za0, za1, oa0, oa1;
-      if (c1 == 0) { za0 = x0; za1 = x1; oa0 = oa1 = 0; }
-      else if (c1 == x) { oa0 = x0; oa1 = x1; za0 = za1 = 0; }
-      else {
-        const uint32_t c0 = x - c1;
-        za0 = z0; za1 = c0 - z0;
-        oa1 = x1 - za1; oa0 = c1 - oa1;
-        if (fe) {
-          const uint32_t lo = x0 > c1 ? x0 - c1 : 0u;
-          const uint32_t hi = x0 - (c1 > x1 ? c1 - x1 : 0u);
-          const unsigned long long pe = cursor + (uint32_t(excl >> 42) & 0x1FFFFFu);
-          if (pe < a.ecap[l]) {
-            bce_tuple t;
-            t.sym = za0 - lo; t.k = hi - lo + 1; t.c1 = c0; t.c2 = x1; t.cs = x;      // bce.cpp:1302
-            a.emit[l][pe] = t;
-          }
-        }
+      if (nw) {
+        const unsigned long long pe = cursor + (uint32_t(excl >> 42) & 0x1FFFFFu);
+        if (pe + nw <= a.ecap[l]) put_words(a.emit[l] + pe, nw, e0, e1, e2, x1, x);
       }
       if (fz) { const uint32_t at = uint32_t(excl) & 0x1FFFFFu; rs[at] = s0; ra[at] = za0; rb[at] = za1; }
       if (fo) { const uint32_t at = tz + (uint32_t(excl >> 21) & 0x1FFFFFu); rs[at] = a.C[ln] + s1; ra[at] = oa0; rb[at] = oa1; }
@@ -548,6 +348,30 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_n
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
+struct CseHost {
+  CseArgs args;
+  uint32_t n = 0;
+  bool narrow = true;                    // which kernel runs next (the root frontier is narrow)
+  uint32_t last_round = 0;
+  // wide kernel variants: [0] = 2 nodes per thread (512-node tiles), [1] = 4 (1024-node tiles)
+  const void* var_fn[2] = {nullptr, nullptr};
+  size_t var_smem[2] = {0, 0};
+  int var_grid[2] = {0, 0};
+  int fixed_items = 0;                   // 0 = pick by frontier size
+  unsigned long long known_nodes = 0;    // frontier size after the last launch
+  // emission: one or two sets of device buffers (two = copy of batch k overlaps compute of k+1)
+  int sets = 1;
+  uint32_t* emit_dev[2][8] = {};
+  size_t ecap_words = 0;
+  int fill_set = 0;                      // set the kernels write next
+  // a computed batch waiting to be copied out / returned
+  bool pending = false, pending_done = false;
+  int pending_set = 0;
+  size_t pending_cnt[8] = {};
+  int pinned_flip = 0;
+  bool finished = false;                 // the level loop terminated
+};
+
 static size_t env_size(const char* name, size_t dflt) {
   const char* v = getenv(name);
   if (!v || !*v) return dflt;
@@ -566,33 +390,30 @@ int cse_begin(Ctx* c, uint32_t n) {
   CseHost* H = c->cse;
   H->n = n;
   cudaStream_t st = c->stream;
+  CseArgs& a = H->args;
+  a.emit_mode = c->emit_mode;
+  memcpy(a.cfgbits, c->emit_cfg, sizeof a.cfgbits);
+  const size_t wmax = a.emit_mode == kEmitRaw ? 5 : 2;
 
   // ---- sizing: frontier first (correctness), emission with what is left ------------
   const size_t budget = scratch_budget(c);
   const size_t cap_full = ((size_t(n) / 2 + 4) + 3) & ~size_t(3);
   size_t cap = cap_full;
   auto frontier_bytes = [](size_t cp) { return 48 * Carver::need(cp, 4); };
-  const int items = int(env_size("BCE_GPU_CSE_ITEMS", 0));
-  H->auto_items = items == 0 && env_size("BCE_GPU_CSE_DIRECT", 0) == 0;
-  H->items = (items == 1 || items == 4) ? items : 2;
-  H->known_nodes = 0;
-  const size_t tile = size_t(CS_THREADS);          // descriptors sized for the smallest tile of any variant
-  auto desc_tiles_for = [tile](size_t cp) { return 8 * (cp / tile + 2); };
   while (cap > 4096 && frontier_bytes(cap) > budget / 2) cap = (cap / 2 + 3) & ~size_t(3);
-  const size_t desc_tiles = desc_tiles_for(cap);
+  const size_t desc_tiles = 8 * (cap / CS_THREADS + 2);      // sized for the smallest tile of any variant
   const size_t desc_bytes = Carver::need(3 * desc_tiles, 8);
-  const size_t pinned_limit = env_size("BCE_GPU_PINNED_LIMIT", size_t(8) << 30);
-  size_t left = budget > frontier_bytes(cap) + desc_bytes ? budget - frontier_bytes(cap) - desc_bytes : 0;
-  size_t ecap = size_t(n);                                  // a level emits at most n-1 counts in total
-  const size_t per_level_min = cap + CS_MAX_TILE;           // one round must always fit
-  if (ecap * 8 * sizeof(bce_tuple) > left) ecap = left / (8 * sizeof(bce_tuple));
-  if (ecap * 8 * sizeof(bce_tuple) > pinned_limit) ecap = pinned_limit / (8 * sizeof(bce_tuple));
-  if (ecap < per_level_min) ecap = per_level_min;
-  const size_t need = frontier_bytes(cap) + desc_bytes + 8 * Carver::need(ecap, sizeof(bce_tuple)) + 4096;
+  const size_t left = budget > frontier_bytes(cap) + desc_bytes ? budget - frontier_bytes(cap) - desc_bytes : 0;
+  H->sets = (c->cse_resident || env_size("BCE_GPU_NO_OVERLAP", 0)) ? 1 : 2;
+  const size_t pinned_limit = env_size("BCE_GPU_PINNED_LIMIT", size_t(4) << 30);   // per pinned buffer (two are used)
+  size_t ew = size_t(n) * wmax;                              // a level emits at most n-1 counts in total
+  const size_t per_level_min = (cap + CS_MAX_TILE) * wmax;   // one round must always fit
+  if (ew * 8 * 4 * H->sets > left) ew = left / (8 * 4 * H->sets);
+  if (!c->cse_resident && ew * 8 * 4 > pinned_limit) ew = pinned_limit / (8 * 4);
+  if (ew < per_level_min) ew = per_level_min;
+  const size_t need = frontier_bytes(cap) + desc_bytes + size_t(H->sets) * 8 * Carver::need(ew, 4) + 4096;
   BCE_TRY(c->scratch.ensure(c, need));
   Carver cv(c->scratch.p, c->scratch.cap);
-
-  CseArgs& a = H->args;
   for (int p = 0; p < 2; ++p)
     for (int l = 0; l < 8; ++l) {
       a.fs[p][l] = cv.take<uint32_t>(cap);
@@ -600,8 +421,12 @@ int cse_begin(Ctx* c, uint32_t n) {
       a.fb[p][l] = cv.take<uint32_t>(cap);
     }
   a.desc = cv.take<uint64_t>(3 * desc_tiles);
-  for (int l = 0; l < 8; ++l) { a.emit[l] = cv.take<bce_tuple>(ecap); a.ecap[l] = ecap; }
+  for (int s = 0; s < H->sets; ++s)
+    for (int l = 0; l < 8; ++l) H->emit_dev[s][l] = cv.take<uint32_t>(ew);
   if (!cv.ok()) { set_error(c, "cse_begin: scratch carve failed (need %zu)", need); return BCE_GPU_E_NOMEM; }
+  H->ecap_words = ew;
+  H->fill_set = 0;
+  for (int l = 0; l < 8; ++l) { a.emit[l] = H->emit_dev[0][l]; a.ecap[l] = ew; }
   const size_t words = size_t(n) / 32 + 1;
   for (int l = 0; l < 8; ++l) { a.ranks[l] = c->ranks.as<uint64_t>() + size_t(l) * words; a.C[l] = c->C[l]; }
   a.cap = uint32_t(cap);
@@ -612,83 +437,57 @@ int cse_begin(Ctx* c, uint32_t n) {
   a.dbg = 0;
   a.min_nodes = 0;
   a.max_nodes = ~0ull;
-  H->narrow = a.use_narrow != 0;
-  H->last_round = 0;
   a.st = reinterpret_cast<CseDeviceState*>(c->small.as<char>() + kSmallCse);
   static_assert(sizeof(CseDeviceState) <= 1024, "state must fit its slot in Ctx::small");
+  H->narrow = a.use_narrow != 0;
+  H->last_round = 0;
+  H->known_nodes = 0;
+  H->pending = H->pending_done = H->finished = false;
+  const int items = int(env_size("BCE_GPU_CSE_ITEMS", 0));
+  H->fixed_items = (items == 2 || items == 4) ? items : 0;
 
   BCE_CUDA(c, cudaMemsetAsync(a.desc, 0, 3 * desc_tiles * sizeof(uint64_t), st));
   cse_init_kernel<<<1, 32, 0, st>>>(a, n);
   c->stats.gpu_launches++;
   BCE_CUDA(c, cudaGetLastError());
 
-  {
-    int per_sm = 0;
-    const bool direct = env_size("BCE_GPU_CSE_DIRECT", 0) != 0 || H->items == 1;   // unpipelined variant
-    H->wide_smem = 0;
-    if (!direct && H->items == 4) {
-      H->wide_fn = (const void*)cse_wide_kernel<4>;
-      H->wide_smem = 2 * sizeof(WideStage<4>);
-      BCE_CUDA(c, cudaFuncSetAttribute(cse_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->wide_smem)));
-      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cse_wide_kernel<4>, CS_THREADS, H->wide_smem));
-    } else if (!direct) {
-      H->wide_fn = (const void*)cse_wide_kernel<2>;
-      H->wide_smem = 2 * sizeof(WideStage<2>);
-      BCE_CUDA(c, cudaFuncSetAttribute(cse_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->wide_smem)));
-      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cse_wide_kernel<2>, CS_THREADS, H->wide_smem));
-    } else if (H->items == 4) {
-      H->wide_fn = (const void*)cse_rounds_kernel<4>;
-      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cse_rounds_kernel<4>, CS_THREADS, 0));
-    } else if (H->items == 1) {
-      H->wide_fn = (const void*)cse_rounds_kernel<1>;
-      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cse_rounds_kernel<1>, CS_THREADS, 0));
-    } else {
-      H->wide_fn = (const void*)cse_rounds_kernel<2>;
-      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cse_rounds_kernel<2>, CS_THREADS, 0));
-    }
-    if (per_sm < 1) { set_error(c, "cse kernel does not fit on an SM"); return BCE_GPU_E_CUDA; }
-    H->grid = per_sm * c->sm_count;
-    if (H->auto_items) {
-      int p2 = 0, p4 = 0;
-      H->var_fn[0] = (const void*)cse_wide_kernel<2>; H->var_smem[0] = 2 * sizeof(WideStage<2>);
-      H->var_fn[1] = (const void*)cse_wide_kernel<4>; H->var_smem[1] = 2 * sizeof(WideStage<4>);
-      BCE_CUDA(c, cudaFuncSetAttribute(cse_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->var_smem[0])));
-      BCE_CUDA(c, cudaFuncSetAttribute(cse_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->var_smem[1])));
-      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, cse_wide_kernel<2>, CS_THREADS, H->var_smem[0]));
-      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p4, cse_wide_kernel<4>, CS_THREADS, H->var_smem[1]));
-      if (p2 < 1 || p4 < 1) { set_error(c, "cse kernel does not fit on an SM"); return BCE_GPU_E_CUDA; }
-      H->var_grid[0] = p2 * c->sm_count;
-      H->var_grid[1] = p4 * c->sm_count;
-    }
+  if (!H->var_fn[0]) {
+    int p2 = 0, p4 = 0;
+    H->var_fn[0] = (const void*)cse_wide_kernel<2>; H->var_smem[0] = 2 * sizeof(WideStage<2>);
+    H->var_fn[1] = (const void*)cse_wide_kernel<4>; H->var_smem[1] = 2 * sizeof(WideStage<4>);
+    BCE_CUDA(c, cudaFuncSetAttribute(cse_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->var_smem[0])));
+    BCE_CUDA(c, cudaFuncSetAttribute(cse_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->var_smem[1])));
+    BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, cse_wide_kernel<2>, CS_THREADS, H->var_smem[0]));
+    BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p4, cse_wide_kernel<4>, CS_THREADS, H->var_smem[1]));
+    if (p2 < 1 || p4 < 1) { H->var_fn[0] = nullptr; set_error(c, "cse kernel does not fit on an SM"); return BCE_GPU_E_CUDA; }
+    H->var_grid[0] = p2 * c->sm_count;
+    H->var_grid[1] = p4 * c->sm_count;
   }
   c->cse_active = true;
   c->cse_done = false;
-  BCE_TRACE("cse_begin n=%u cap=%zu ecap=%zu grid=%d", n, cap, ecap, H->grid);
+  BCE_TRACE("cse_begin n=%u cap=%zu ecap_words=%zu sets=%d mode=%u grids=%d/%d", n, cap, ew, H->sets, a.emit_mode,
+            H->var_grid[0], H->var_grid[1]);
   return BCE_GPU_OK;
 }
 
-// Runs rounds until the loop ends or an emission buffer may overflow; resident = leave the
-// counts in device memory (measurement), otherwise copy them to pinned host memory.
-int cse_advance(Ctx* c, bool resident, bce_cse_batch* out) {
-  if (!c->cse_active || !c->cse) { set_error(c, "cse_next without cse_begin"); return BCE_GPU_E_STATE; }
+// Runs kernels until the level loop ends or an emission buffer of set `set` may overflow.
+// On return cnt[l] = words emitted into that set, *done = loop finished.
+static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
   CseHost* H = c->cse;
   cudaStream_t st = c->stream;
-  if (out) memset(out, 0, sizeof *out);
-  if (c->cse_done) { if (out) out->done = 1; return BCE_GPU_OK; }
-
   CseDeviceState* h_state = reinterpret_cast<CseDeviceState*>(c->pinned_small.as<char>() + 40 * 1024);
+  for (int l = 0; l < 8; ++l) H->args.emit[l] = H->emit_dev[set][l];
   BCE_CUDA(c, cudaEventRecord(c->ev[2], st));
-  float ms = 0;
   for (int hops = 0;; ++hops) {
     if (hops > 100000) { set_error(c, "cse: wide/narrow ping-pong"); return BCE_GPU_E_INTERNAL; }
     const bool was_narrow = H->narrow;
     BCE_CUDA(c, cudaEventRecord(c->ev[0], st));
-    {
+    {   // timing experiments (BCE_GPU_CSE_DBG_ROUND / _FLAGS): run one chosen round with parts off
       const uint32_t dbg_round = uint32_t(env_size("BCE_GPU_CSE_DBG_ROUND", 0));
       H->args.max_rounds = 0x7FFFFFFFu;
       H->args.dbg = 0;
       if (dbg_round && !H->narrow) {
-        if (H->last_round < dbg_round) H->args.max_rounds = dbg_round - H->last_round;   // stop right before it
+        if (H->last_round < dbg_round) H->args.max_rounds = dbg_round - H->last_round;
         else if (H->last_round == dbg_round) { H->args.max_rounds = 1; H->args.dbg = uint32_t(env_size("BCE_GPU_CSE_DBG_FLAGS", 0)); }
       }
     }
@@ -696,19 +495,19 @@ int cse_advance(Ctx* c, bool resident, bce_cse_batch* out) {
       cse_narrow_kernel<<<8, NR_THREADS, 0, st>>>(H->args);
       BCE_CUDA(c, cudaGetLastError());
     } else {
-      const void* fn = H->wide_fn;
-      size_t smem = H->wide_smem;
-      int grid = H->grid;
+      // 1024-node tiles while the frontier is huge, 512-node tiles below (more CTAs per round)
+      constexpr unsigned long long kBig = 2000000, kLeaveBig = 1000000, kLeaveSmall = 3000000;
       H->args.min_nodes = 0;
       H->args.max_nodes = ~0ull;
-      if (H->auto_items) {
-        constexpr unsigned long long kBig = 2000000, kLeaveBig = 1000000, kLeaveSmall = 3000000;
-        const int v = H->known_nodes >= kBig ? 1 : 0;
-        fn = H->var_fn[v]; smem = H->var_smem[v]; grid = H->var_grid[v];
+      int v;
+      if (H->fixed_items) v = H->fixed_items == 4 ? 1 : 0;
+      else {
+        v = H->known_nodes >= kBig ? 1 : 0;
         if (v) H->args.min_nodes = kLeaveBig; else H->args.max_nodes = kLeaveSmall;
       }
       void* kargs[] = {&H->args};
-      BCE_CUDA(c, cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(CS_THREADS), kargs, smem, st));
+      BCE_CUDA(c, cudaLaunchCooperativeKernel(H->var_fn[v], dim3(H->var_grid[v]), dim3(CS_THREADS), kargs,
+                                              H->var_smem[v], st));
     }
     c->stats.gpu_launches++;
     c->stats.cse_launches++;
@@ -723,8 +522,6 @@ int cse_advance(Ctx* c, bool resident, bce_cse_batch* out) {
                 H->last_round, h_state->round, h_state->status, h_state->err, h_state->visits, lms, H->args.dbg);
       if (H->args.dbg) { set_error(c, "cse: timing experiment round done (%.3f ms)", lms); return BCE_GPU_E_INTERNAL; }
       H->last_round = h_state->round;
-    }
-    {
       const int par = h_state->round & 1;
       H->known_nodes = 0;
       for (int l = 0; l < 8; ++l) H->known_nodes += h_state->cnt[par][l][0] + h_state->cnt[par][l][1];
@@ -737,13 +534,14 @@ int cse_advance(Ctx* c, bool resident, bce_cse_batch* out) {
   }
   BCE_CUDA(c, cudaEventRecord(c->ev[3], st));
   BCE_CUDA(c, cudaEventSynchronize(c->ev[3]));
+  float ms = 0;
   BCE_CUDA(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
   c->stats.ms_cse += ms;
 
   if (h_state->err) {
-    set_error(c, "cse: %s watchdog fired (round %u, barrier_fail %u, arrivals %llu, barriers %llu, grid %d)",
+    set_error(c, "cse: %s watchdog fired (round %u, barrier_fail %u, arrivals %llu, barriers %llu)",
               h_state->err == 2 ? "grid-barrier" : "chained-scan", h_state->round, h_state->barrier_fail,
-              h_state->arrivals, h_state->barriers, H->grid);
+              h_state->arrivals, h_state->barriers);
     return BCE_GPU_E_INTERNAL;
   }
   if (h_state->status == kCseRunaway) {
@@ -759,42 +557,88 @@ int cse_advance(Ctx* c, bool resident, bce_cse_batch* out) {
     return BCE_GPU_E_INTERNAL;
   }
   const int par = h_state->round & 1;
-  size_t total = 0, cnt[8];
+  size_t total = 0;
   for (int l = 0; l < 8; ++l) { cnt[l] = size_t(h_state->emitted[par][l]); total += cnt[l]; }
   if (h_state->status == kCseDrain && total == 0) {
     set_error(c, "cse: kernel asked to drain empty emission buffers at round %u", h_state->round);
     return BCE_GPU_E_INTERNAL;
   }
-  c->stats.cse_tuples += total;
+  c->stats.cse_words += total;
+  if (H->args.emit_mode == kEmitRaw) c->stats.cse_tuples += total / 5;
   c->stats.cse_visits = h_state->visits;
   c->stats.cse_rounds = h_state->round ? h_state->round : 1;   // the reference's do..while runs at least once
   c->stats.cse_peak_frontier = h_state->peak_frontier;
-
-  if (!resident && out) {
-    BCE_TRY(c->pinned_emit.ensure(c, (total + 8) * sizeof(bce_tuple)));
-    bce_tuple* hp = c->pinned_emit.as<bce_tuple>();
-    BCE_CUDA(c, cudaEventRecord(c->ev[2], st));
-    size_t at = 0;
-    for (int l = 0; l < 8; ++l) {
-      out->tuples[l] = hp + at;
-      out->count[l] = cnt[l];
-      if (cnt[l])
-        BCE_CUDA(c, cudaMemcpyAsync(hp + at, H->args.emit[l], cnt[l] * sizeof(bce_tuple), cudaMemcpyDeviceToHost, st));
-      at += cnt[l];
-    }
-    BCE_CUDA(c, cudaEventRecord(c->ev[3], st));
-    BCE_CUDA(c, cudaEventSynchronize(c->ev[3]));
-    BCE_CUDA(c, cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]));
-    c->stats.ms_d2h += ms;
-  }
-  if (h_state->status == kCseDone) {
-    c->cse_done = true;
-    if (out) out->done = 1;
+  *done = h_state->status == kCseDone;
+  if (*done) {
+    H->finished = true;
   } else {
     cse_reset_emitted_kernel<<<1, 32, 0, st>>>(H->args.st);
     c->stats.gpu_launches++;
     BCE_CUDA(c, cudaGetLastError());
   }
+  return BCE_GPU_OK;
+}
+
+// One batch of emitted words.  resident: counts stay in device memory (measurement), the
+// whole loop runs here.  Otherwise a batch is copied to pinned host memory on the copy stream
+// while the kernels already fill the other buffer set with the next batch.
+int cse_advance(Ctx* c, bool resident, CseWordBatch* out) {
+  if (!c->cse_active || !c->cse) { set_error(c, "cse_next without cse_begin"); return BCE_GPU_E_STATE; }
+  CseHost* H = c->cse;
+  if (out) memset(out, 0, sizeof *out);
+  if (c->cse_done) { if (out) out->done = 1; return BCE_GPU_OK; }
+
+  if (resident) {
+    size_t cnt[8];
+    bool done = false;
+    BCE_TRY(run_batch(c, 0, cnt, &done));
+    if (done) c->cse_done = true;
+    return BCE_GPU_OK;
+  }
+  if (!out) return BCE_GPU_E_ARG;
+
+  if (!H->pending) {                                    // first call: nothing computed yet
+    BCE_TRY(run_batch(c, H->fill_set, H->pending_cnt, &H->pending_done));
+    H->pending = true;
+    H->pending_set = H->fill_set;
+    if (H->sets == 2) H->fill_set ^= 1;
+  }
+  // copy the pending batch out on the copy stream ...
+  size_t total = 0;
+  for (int l = 0; l < 8; ++l) total += H->pending_cnt[l];
+  PinnedBuf& pin = H->pinned_flip ? c->pinned_emit2 : c->pinned_emit;
+  H->pinned_flip ^= 1;
+  BCE_TRY(pin.ensure(c, (total + 16) * sizeof(uint32_t)));
+  uint32_t* hp = pin.as<uint32_t>();
+  cudaStream_t cs = c->copy_stream;
+  BCE_CUDA(c, cudaEventRecord(c->ev[6], c->stream));            // everything computed so far ...
+  BCE_CUDA(c, cudaStreamWaitEvent(cs, c->ev[6], 0));            // ... is visible to the copies
+  BCE_CUDA(c, cudaEventRecord(c->ev[4], cs));
+  size_t at = 0;
+  for (int l = 0; l < 8; ++l) {
+    out->words[l] = hp + at;
+    out->count[l] = H->pending_cnt[l];
+    if (H->pending_cnt[l])
+      BCE_CUDA(c, cudaMemcpyAsync(hp + at, H->emit_dev[H->pending_set][l], H->pending_cnt[l] * sizeof(uint32_t),
+                                  cudaMemcpyDeviceToHost, cs));
+    at += H->pending_cnt[l];
+  }
+  BCE_CUDA(c, cudaEventRecord(c->ev[5], cs));
+  const bool this_done = H->pending_done;
+  H->pending = false;
+  // ... and meanwhile compute the next one into the other set
+  if (!this_done && H->sets == 2) {
+    BCE_TRY(run_batch(c, H->fill_set, H->pending_cnt, &H->pending_done));
+    H->pending = true;
+    H->pending_set = H->fill_set;
+    H->fill_set ^= 1;
+  }
+  BCE_CUDA(c, cudaEventSynchronize(c->ev[5]));
+  float ms = 0;
+  BCE_CUDA(c, cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]));
+  c->stats.ms_d2h += ms;
+  out->done = this_done ? 1 : 0;
+  if (this_done) c->cse_done = true;
   return BCE_GPU_OK;
 }
 

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
         }
         nodes += lvl;
         widest = max(widest, uint32_t(min(lvl, 0xFFFFFFFFull)));
-        if (s_emitted[l] + lvl > a.ecap[l]) drain = 1;
+        if (s_emitted[l] + lvl * max_words(a) > a.ecap[l]) drain = 1;   // a round emits at most one count per node
       }
       // tiles per level, ascending, and the number of tiles scheduled before every breakpoint
       for (int l = 0; l < 8; ++l) s_lt[l] = (s_cnt[l][0] + TILE - 1) / TILE + (s_cnt[l][1] + TILE - 1) / TILE;
@@ -189,10 +189,11 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
         const uint32_t one_base = a.C[(l + 1) & 7];
         uint32_t fz = 0, fo = 0, fe = 0;
         uint32_t zs_[ITEMS], za0_[ITEMS], za1_[ITEMS], os_[ITEMS], oa0_[ITEMS], oa1_[ITEMS];
-        uint32_t esym[ITEMS], ek[ITEMS], ec1[ITEMS];
+        uint32_t e0_[ITEMS], e1_[ITEMS], e2_[ITEMS], nw_[ITEMS];          // emitted words (see count_words)
+        uint32_t nwords = 0;
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-          zs_[j] = za0_[j] = za1_[j] = os_[j] = oa0_[j] = oa1_[j] = esym[j] = ek[j] = ec1[j] = 0;
+          zs_[j] = za0_[j] = za1_[j] = os_[j] = oa0_[j] = oa1_[j] = e0_[j] = e1_[j] = e2_[j] = nw_[j] = 0;
           if (j < nv) {
             const uint32_t s = ns[j], x0 = na[j], x1 = nb[j], x = x0 + x1;
             const uint32_t s1 = rank1_word(wa[j], s);
@@ -208,13 +209,17 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
               const uint32_t lo = x0 > c1 ? x0 - c1 : 0u;                     // :1290-1294
               const uint32_t hi = x0 - (c1 > x1 ? c1 - x1 : 0u);
               const uint32_t z1 = c0 - z0, o1 = x1 - z1, o0c = c1 - o1;       // _0x1, _1x1, _1x0
-              if (hi != lo) { fe |= 1u << j; esym[j] = z0 - lo; ek[j] = hi - lo + 1; ec1[j] = c0; }   // :1302
+              if (hi != lo) {                                                  // :1302
+                fe |= 1u << j;
+                nw_[j] = count_words(a, l, z0 - lo, hi - lo + 1, c0, x1, x, e0_[j], e1_[j], e2_[j]);
+                nwords += nw_[j];
+              }
               if (z0 && z1) { fz |= 1u << j; za0_[j] = z0; za1_[j] = z1; }    // :1338
               if (o0c && o1) { fo |= 1u << j; oa0_[j] = o0c; oa1_[j] = o1; }  // :1345
             }
           }
         }
-        const uint64_t mine = uint64_t(__popc(fz)) | (uint64_t(__popc(fo)) << 21) | (uint64_t(__popc(fe)) << 42);
+        const uint64_t mine = uint64_t(__popc(fz)) | (uint64_t(__popc(fo)) << 21) | (uint64_t(nwords) << 42);
         uint64_t tile_tot;
         const uint64_t excl = block_exclusive_scan<uint64_t, CS_THREADS>(mine, s_scan, tile_tot);
         c_valid = true;
@@ -239,9 +244,8 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
             if (fz >> j & 1u) { st.zs[lz] = zs_[j]; st.za[lz] = za0_[j]; st.zb[lz] = za1_[j]; ++lz; }
             if (fo >> j & 1u) { st.os[lo_] = os_[j]; st.oa[lo_] = oa0_[j]; st.ob[lo_] = oa1_[j]; ++lo_; }
             if (fe >> j & 1u) {
-              uint32_t* e = st.e + le * 5;
-              e[0] = esym[j]; e[1] = ek[j]; e[2] = ec1[j]; e[3] = nb[j]; e[4] = na[j] + nb[j];
-              ++le;
+              put_words(st.e + le, nw_[j], e0_[j], e1_[j], e2_[j], nb[j], na[j] + nb[j]);
+              le += nw_[j];
             }
           }
         }
@@ -287,8 +291,8 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
           if (ord < a.cap) { const uint32_t at = a.cap - 1 - ord; gs[at] = st.os[j]; ga[at] = st.oa[j]; gb[at] = st.ob[j]; }
         }
         if (pe + p_te <= a.ecap[p_l]) {
-          uint32_t* __restrict__ ew = reinterpret_cast<uint32_t*>(a.emit[p_l] + pe);
-          for (uint32_t w = tid; w < p_te * 5 * fl; w += CS_THREADS) ew[w] = st.e[w];
+          uint32_t* __restrict__ ew = a.emit[p_l] + pe;
+          for (uint32_t w = tid; w < p_te * fl; w += CS_THREADS) ew[w] = st.e[w];
         }
         if (p_last && tid == 0) {
           S->cnt[nxt][ln][0] = pz + p_tz;

@@ -31,7 +31,8 @@ struct Ctx : bce_gpu_ctx {
   DevBuf small;       // counters, histograms, descriptors' tickets, state structs
   DevBuf desc;        // tile descriptors (tagged, never cleared between passes)
   PinnedBuf pinned_small;   // host mirror for small read-backs
-  PinnedBuf pinned_emit;    // emitted counts handed to the caller
+  PinnedBuf pinned_emit;    // emitted counts handed to the caller (two buffers alternate)
+  PinnedBuf pinned_emit2;
   PinnedBuf pinned_io;      // staging for pageable caller buffers
 
   uint32_t desc_tag = 0;    // monotonically increasing pass tag (30 bits used)
@@ -43,6 +44,12 @@ struct Ctx : bce_gpu_ctx {
   bool ranks_resident = false;
   uint32_t offset = 0;
   uint32_t C[8] = {};
+
+  // emission format for the next cse_begin (bce_gpu_set_emit_mode)
+  uint32_t emit_mode = 0;
+  uint8_t emit_cfg[8][32] = {};
+  bool cse_resident = false;   // counts stay in device memory (front_resident)
+  int cse_emit_mode_active = 0; // mode the current run was started with
 
   // CSE run state (host side)
   bool cse_active = false;
@@ -78,7 +85,8 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host_or_null);
 int wavelet_build(Ctx* c, uint32_t n);
 // cse.cu
 int cse_begin(Ctx* c, uint32_t n);
-int cse_advance(Ctx* c, bool resident, bce_cse_batch* out);
+struct CseWordBatch { const uint32_t* words[8]; size_t count[8]; int done; };
+int cse_advance(Ctx* c, bool resident, CseWordBatch* out);
 void cse_destroy(Ctx* c);
 // unbwt.cu
 int unbwt_run(Ctx* c, uint32_t offset, uint32_t n, uint8_t* out_host);

@@ -28,6 +28,17 @@ void ArchiveWriter::feed(const bce_cse_batch& batch, int threads) {
   for (auto& t : pool) t.join();
 }
 
+void ArchiveWriter::feed_words(const bce_cse_words& batch, int threads) {
+  if (threads <= 1) {
+    for (int i = 0; i < 8; ++i) streams_[i]->packed(batch.words[i], batch.count[i]);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int i = 0; i < 8; ++i)
+    if (batch.count[i]) pool.emplace_back([this, &batch, i] { streams_[i]->packed(batch.words[i], batch.count[i]); });
+  for (auto& t : pool) t.join();
+}
+
 std::vector<uint16_t> ArchiveWriter::finish(uint32_t offset) {
   uint32_t total = 0;
   for (auto& s : streams_) {                                        // bce.cpp:1134-1138
@@ -63,6 +74,10 @@ void ScanSession::feed(const bce_cse_batch& batch) {
     const bce_tuple* t = batch.tuples[i];
     for (size_t j = 0; j < batch.count[i]; ++j) streams_[i]->count(t[j].sym, t[j].k, t[j].c1, t[j].c2, t[j].cs);
   }
+}
+
+void ScanSession::feed_words(const bce_cse_words& batch) {
+  for (int i = 0; i < 8; ++i) streams_[i]->packed(batch.words[i], batch.count[i]);
 }
 
 ConfigTable ScanSession::finish() {

@@ -14,6 +14,7 @@ class ArchiveWriter {
   ArchiveWriter(uint32_t n, const uint32_t C[8], const ConfigTable& cfg);
   // codes the batch; with threads > 1 every stream runs on its own thread
   void feed(const bce_cse_batch& batch, int threads);
+  void feed_words(const bce_cse_words& batch, int threads);      // BCE_EMIT_CODER batches
   std::vector<uint16_t> finish(uint32_t offset);
 
  private:
@@ -26,6 +27,7 @@ class ScanSession {
  public:
   ScanSession();
   void feed(const bce_cse_batch& batch);
+  void feed_words(const bce_cse_words& batch);                    // BCE_EMIT_SCAN batches
   ConfigTable finish();
 
  private:

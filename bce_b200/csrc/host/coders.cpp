@@ -176,6 +176,42 @@ void StreamEncoder::count(uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2, ui
   ContextModel::bump(row, k, sym);
 }
 
+void StreamEncoder::packed(const uint32_t* words, size_t count) {
+  for (size_t i = 0; i < count; ++i) {
+    const uint32_t w = words[i];
+    if (w >> 31) {                                                  // k > 31: nb uniform bits first (bce.cpp:507-510)
+      const uint32_t nb = (w >> 20) & 31u, low = words[++i];
+      for (uint32_t j = 0; j < nb; ++j) rc_.put_uniform((low >> j) & 1u, 2);
+    }
+    const uint32_t sym = w & 31u, k = (w >> 5) & 31u, ctx = (w >> 10) & 1023u;
+    uint8_t* row = model_.row_at(k, ctx);
+    uint32_t below = sym, total = k;                                // bce.cpp:514-518
+    for (uint32_t j = 0; j < sym; ++j) below += row[j];
+    for (uint32_t j = 0; j < k; ++j) total += row[j];
+    rc_.put(below, uint32_t(row[sym]) + 1, total);
+    ContextModel::bump(row, k, sym);
+  }
+}
+
+size_t pack_count(int mode, const uint8_t* bits_row, uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2,
+                  uint32_t cs, uint32_t out[2]) {
+  uint32_t nb = 0, s = sym;
+  if (mode == 1) {                                                  // BCE_EMIT_CODER
+    while (k > uint32_t(kMaxAdaptive)) { k = (k + (~s & 1u)) >> 1; s >>= 1; ++nb; }
+    const uint32_t b = bits_row[k];
+    const uint32_t ctx = (((c1 << b) / cs) << b) | ((c2 << b) / cs);
+    const uint32_t w = (ctx << 10) | (k << 5) | s;
+    if (!nb) { out[0] = w; return 1; }
+    out[0] = 0x80000000u | (nb << 20) | w;
+    out[1] = sym & ((1u << nb) - 1u);
+    return 2;
+  }
+  while (k > uint32_t(kMaxAdaptive)) { k = (k >> 1) + (~s & 1u); s >>= 1; ++nb; }     // BCE_EMIT_SCAN
+  const uint32_t q1 = (c1 << 8) / cs, q2 = (c2 << 8) / cs;
+  out[0] = (nb ? 0x80000000u | (nb << 26) : 0u) | (q2 << 18) | (q1 << 10) | (k << 5) | s;
+  return 1;
+}
+
 void StreamEncoder::varint(uint32_t v) {                            // bce.cpp:364-370
   for (; v; v >>= 1) rc_.put_uniform(v & 1u, 3);
   rc_.put_uniform(2, 3);
@@ -223,6 +259,16 @@ void ScanCollector::count(uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2, ui
     sym >>= 1;
   }
   stat_[k][(((c2 << 8) / cs) << 16) | ((c1 << 8) / cs)].push_back(uint8_t(sym));   // bce.cpp:743
+}
+
+void ScanCollector::packed(const uint32_t* words, size_t count) {
+  for (size_t i = 0; i < count; ++i) {
+    const uint32_t w = words[i];
+    if (w >> 31)
+      for (uint32_t nb = (w >> 26) & 31u; nb; --nb) nats_ += std::log(2);         // one addition per halving, as :739
+    const uint32_t sym = w & 31u, k = (w >> 5) & 31u, q1 = (w >> 10) & 255u, q2 = (w >> 18) & 255u;
+    stat_[k][(q2 << 16) | q1].push_back(uint8_t(sym));
+  }
 }
 
 void ScanCollector::finish(ConfigTable& table) {                    // bce.cpp:751-800

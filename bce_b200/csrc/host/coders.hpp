@@ -74,6 +74,8 @@ class ContextModel {
     const uint32_t ctx = (((c1 << b) / cs) << b) | ((c2 << b) / cs);
     return stat_.data() + (o & 0x00FFFFFFu) + size_t(ctx) * k;
   }
+  // same counters addressed by a context index computed elsewhere (packed device words)
+  uint8_t* row_at(uint32_t k, uint32_t ctx) { return stat_.data() + (off_[k] & 0x00FFFFFFu) + size_t(ctx) * k; }
   static void bump(uint8_t* row, uint32_t k, uint32_t sym) {      // bce.cpp:531-533
     if (++row[sym] == 0xFF)
       for (uint32_t i = 0; i < k; ++i) row[i] >>= 1;
@@ -91,6 +93,8 @@ class StreamEncoder {
   void uniform(uint32_t sym, uint32_t range) { rc_.put_uniform(sym, range); }
   void count(uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2, uint32_t cs);
   void varint(uint32_t v);                                        // VCoder::setv
+  // BCE_EMIT_CODER words (include/bce_gpu.h): context index and k > 31 halving done on the device
+  void packed(const uint32_t* words, size_t count);
   void finish() { rc_.finish(); }
   const std::vector<uint16_t>& words() const { return rc_.words(); }
 
@@ -113,10 +117,15 @@ class StreamDecoder {
 
 // `bce -s`: records every adaptive symbol per context, then picks for every k the number of
 // context bits (0..5) that minimises the simulated adaptive code length.
+// host-side packer with the device's word formats (tests, and callers that hold raw counts)
+size_t pack_count(int mode, const uint8_t* bits_row, uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2,
+                  uint32_t cs, uint32_t out[2]);
+
 class ScanCollector {
  public:
   explicit ScanCollector(int id) : row_(id < 0 || id > 7 ? 8 : id) {}
   void count(uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2, uint32_t cs);   // bce.cpp:737-744
+  void packed(const uint32_t* words, size_t count);                              // BCE_EMIT_SCAN words
   // bce.cpp:751-800: fills table[row] and prints "Result size: %.1f B"
   void finish(ConfigTable& table);
 

@@ -37,6 +37,23 @@ int bce_archive_feed(bce_archive_writer* h, const bce_cse_batch* batch, int thre
   h->w->feed(*batch, threads);
   return BCE_GPU_OK;
 }
+int bce_archive_feed_words(bce_archive_writer* h, const bce_cse_words* batch, int threads) {
+  if (!h || !batch) return BCE_GPU_E_ARG;
+  h->w->feed_words(*batch, threads);
+  return BCE_GPU_OK;
+}
+int bce_scan_feed_words(bce_scan* h, const bce_cse_words* batch) {
+  if (!h || !batch) return BCE_GPU_E_ARG;
+  h->s->feed_words(*batch);
+  return BCE_GPU_OK;
+}
+size_t bce_host_pack_counts(int mode, const uint8_t* cfg288, int stream, const bce_tuple* t, size_t count, uint32_t* words) {
+  ConfigTable tab = table_from(cfg288);
+  size_t at = 0;
+  for (size_t i = 0; i < count; ++i)
+    at += pack_count(mode, tab[stream].data(), t[i].sym, t[i].k, t[i].c1, t[i].c2, t[i].cs, words + at);
+  return at;
+}
 int bce_archive_finish(bce_archive_writer* h, uint32_t offset, uint16_t** words, size_t* nwords) {
   if (!h || !words || !nwords) return BCE_GPU_E_ARG;
   std::vector<uint16_t> out = h->w->finish(offset);
@@ -80,31 +97,38 @@ int bce_scan_finish(bce_scan* h, uint8_t cfg288_out[288]) {
 int bce_compress_buffer(bce_gpu_ctx* ctx, const uint8_t* T, uint32_t n, const uint8_t* cfg288, int threads,
                         uint16_t** words, size_t* nwords) {
   uint32_t offset = 0, C[8];
-  int rc = bce_gpu_compress_front(ctx, T, n, &offset, C);           // RankFile ctor, bce.cpp:1411
+  // the device emits coder-ready words: context index and k > 31 halving are done there
+  int rc = bce_gpu_set_emit_mode(ctx, BCE_EMIT_CODER, cfg288);
   if (rc) return rc;
+  rc = bce_gpu_compress_front(ctx, T, n, &offset, C);               // RankFile ctor, bce.cpp:1411
+  if (rc) { bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return rc; }
   bce_archive_writer* w = bce_archive_begin(n, C, cfg288);          // BCE::encode, bce.cpp:1417
-  if (!w) return BCE_GPU_E_NOMEM;
-  bce_cse_batch batch;
+  if (!w) { bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return BCE_GPU_E_NOMEM; }
+  bce_cse_words batch;
   do {
-    rc = bce_gpu_cse_next(ctx, &batch);
-    if (rc) { bce_archive_abort(w); return rc; }
-    bce_archive_feed(w, &batch, threads);
+    rc = bce_gpu_cse_next_words(ctx, &batch);
+    if (rc) { bce_archive_abort(w); bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return rc; }
+    bce_archive_feed_words(w, &batch, threads);
   } while (!batch.done);
+  bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr);
   return bce_archive_finish(w, offset, words, nwords);
 }
 
 int bce_scan_buffer(bce_gpu_ctx* ctx, const uint8_t* T, uint32_t n, uint8_t cfg288_out[288]) {
   uint32_t offset = 0, C[8];
-  int rc = bce_gpu_compress_front(ctx, T, n, &offset, C);
+  int rc = bce_gpu_set_emit_mode(ctx, BCE_EMIT_SCAN, nullptr);
   if (rc) return rc;
+  rc = bce_gpu_compress_front(ctx, T, n, &offset, C);
+  if (rc) { bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return rc; }
   bce_scan* s = bce_scan_begin();
-  if (!s) return BCE_GPU_E_NOMEM;
-  bce_cse_batch batch;
+  if (!s) { bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return BCE_GPU_E_NOMEM; }
+  bce_cse_words batch;
   do {
-    rc = bce_gpu_cse_next(ctx, &batch);
-    if (rc) { delete s->s; delete s; return rc; }
-    bce_scan_feed(s, &batch);
+    rc = bce_gpu_cse_next_words(ctx, &batch);
+    if (rc) { delete s->s; delete s; bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return rc; }
+    bce_scan_feed_words(s, &batch);
   } while (!batch.done);
+  bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr);
   return bce_scan_finish(s, cfg288_out);
 }
 #endif

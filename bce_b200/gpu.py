@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "bce_gpu_last_error", "bce_gpu_get_stats", "bce_gpu_set_scratch_limit", "bce_gpu_bwt",
     "bce_gpu_wavelet", "bce_gpu_cse_begin", "bce_gpu_cse_next", "bce_gpu_compress_front",
     "bce_gpu_stage_input", "bce_gpu_front_resident", "bce_gpu_unbwt",
+    "bce_gpu_set_emit_mode", "bce_gpu_cse_next_words",
 ]
 
 
@@ -43,6 +44,13 @@ class CseBatch(C.Structure):
     _fields_ = [("tuples", C.POINTER(Tuple5) * 8), ("count", C.c_size_t * 8), ("done", C.c_int)]
 
 
+class CseWords(C.Structure):
+    _fields_ = [("words", C.POINTER(C.c_uint32) * 8), ("count", C.c_size_t * 8), ("done", C.c_int)]
+
+
+EMIT_RAW, EMIT_CODER, EMIT_SCAN = 0, 1, 2
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("n", C.c_uint32), ("sort_rounds", C.c_uint32),
@@ -57,6 +65,7 @@ class Stats(C.Structure):
         ("ms_unbwt_bytes", C.c_float), ("ms_unbwt_chase", C.c_float),
         ("ms_bwt_total", C.c_float), ("ms_cse_total", C.c_float), ("ms_total", C.c_float),
         ("ms_cse_narrow", C.c_float), ("cse_rounds_narrow", C.c_uint32), ("ms_radix_kernel", C.c_float),
+        ("cse_words", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
@@ -98,6 +107,8 @@ def load_library() -> C.CDLL:
     lib.bce_gpu_stage_input.argtypes = [vp, vp, u32]
     lib.bce_gpu_front_resident.argtypes = [vp, u32p, C.POINTER(C.c_uint64)]
     lib.bce_gpu_unbwt.argtypes = [vp, C.POINTER(vp), u32, u32, vp]
+    lib.bce_gpu_set_emit_mode.argtypes = [vp, C.c_int, vp]
+    lib.bce_gpu_cse_next_words.argtypes = [vp, C.POINTER(CseWords)]
     _lib = lib
     return lib
 
@@ -204,17 +215,47 @@ class Frontend:
         streams, _ = self._drain()
         return int(off.value), [int(x) for x in Cv], streams
 
+    def set_emit_mode(self, mode: int, cfg: bytes | None = None):
+        """EMIT_RAW (20-byte counts), EMIT_CODER or EMIT_SCAN (packed words, include/bce_gpu.h)."""
+        buf = np.frombuffer(cfg, dtype=np.uint8) if cfg is not None else None
+        self._check(self.lib.bce_gpu_set_emit_mode(self.h, mode, buf.ctypes.data if buf is not None else None))
+
+    def compress_front_words(self, data, mode: int = EMIT_CODER, cfg: bytes | None = None):
+        """Fused front end with packed emission: (offset, C[8], 8 uint32 word arrays)."""
+        T = _as_u8(data)
+        self.set_emit_mode(mode, cfg)
+        try:
+            off = C.c_uint32()
+            Cv = (C.c_uint32 * 8)()
+            self._check(self.lib.bce_gpu_compress_front(self.h, T.ctypes.data, T.size, C.byref(off), Cv))
+            streams = [[] for _ in range(8)]
+            batch = CseWords()
+            while True:
+                self._check(self.lib.bce_gpu_cse_next_words(self.h, C.byref(batch)))
+                for i in range(8):
+                    cnt = int(batch.count[i])
+                    if cnt:
+                        addr = C.addressof(batch.words[i].contents)
+                        streams[i].append(np.ctypeslib.as_array((C.c_uint32 * cnt).from_address(addr)).copy())
+                if batch.done:
+                    break
+        finally:
+            self.set_emit_mode(EMIT_RAW)
+        out = [np.concatenate(s) if s else np.zeros(0, dtype=np.uint32) for s in streams]
+        return int(off.value), [int(x) for x in Cv], out
+
     def compress_front_discard(self, data):
-        """Same call sequence as compress_front, but the emitted counts are only touched in
-        pinned memory, not copied again (bench e2e leg).  Returns (offset, total counts)."""
+        """Same call sequence a consumer makes (fused front end, then batches until done) in the
+        context's current emission mode; the batches are left in pinned memory (bench e2e leg).
+        Returns (offset, total 32-bit words handed back)."""
         T = _as_u8(data)
         off = C.c_uint32()
         Cv = (C.c_uint32 * 8)()
         self._check(self.lib.bce_gpu_compress_front(self.h, T.ctypes.data, T.size, C.byref(off), Cv))
-        batch = CseBatch()
+        batch = CseWords()
         total = 0
         while True:
-            self._check(self.lib.bce_gpu_cse_next(self.h, C.byref(batch)))
+            self._check(self.lib.bce_gpu_cse_next_words(self.h, C.byref(batch)))
             total += sum(int(batch.count[i]) for i in range(8))
             if batch.done:
                 break

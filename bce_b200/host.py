@@ -6,7 +6,7 @@ from pathlib import Path
 
 import numpy as np
 
-from .gpu import CseBatch, Tuple5
+from .gpu import CseBatch, CseWords, Tuple5
 
 _LIB_PATH = Path(__file__).resolve().parent / "libbce_host.so"
 _lib = None
@@ -15,6 +15,7 @@ HOST_SYMBOLS = [
     "bce_archive_begin", "bce_archive_feed", "bce_archive_finish", "bce_archive_abort",
     "bce_scan_begin", "bce_scan_feed", "bce_scan_finish", "bce_compress_buffer", "bce_scan_buffer",
     "bce_host_default_config", "bce_host_free",
+    "bce_archive_feed_words", "bce_scan_feed_words", "bce_host_pack_counts",
 ]
 
 
@@ -37,6 +38,10 @@ def load_library() -> C.CDLL:
         lib.bce_scan_buffer.argtypes = [vp, vp, C.c_uint32, vp]
         lib.bce_host_default_config.restype = vp
         lib.bce_host_free.argtypes = [vp]
+        lib.bce_archive_feed_words.argtypes = [vp, C.POINTER(CseWords), C.c_int]
+        lib.bce_scan_feed_words.argtypes = [vp, C.POINTER(CseWords)]
+        lib.bce_host_pack_counts.argtypes = [C.c_int, vp, C.c_int, vp, C.c_size_t, vp]
+        lib.bce_host_pack_counts.restype = C.c_size_t
         _lib = lib
     return _lib
 
@@ -74,6 +79,61 @@ def encode_archive(Cvals, streams, n: int, offset: int, cfg: bytes | None = None
     out = C.string_at(words.value, nw.value * 2)
     lib.bce_host_free(words)
     return out
+
+
+def pack_counts(mode: int, streams, cfg: bytes | None = None):
+    """Raw (E,5) count streams -> packed word streams with the device's formats (host packer)."""
+    lib = load_library()
+    cfgbuf = np.frombuffer(cfg, dtype=np.uint8) if cfg is not None else None
+    out = []
+    for i, s in enumerate(streams):
+        a = np.ascontiguousarray(s, dtype=np.uint32)
+        w = np.zeros(2 * a.shape[0] + 2, dtype=np.uint32)
+        nw = lib.bce_host_pack_counts(mode, cfgbuf.ctypes.data if cfgbuf is not None else None, i,
+                                      a.ctypes.data, a.shape[0], w.ctypes.data)
+        out.append(w[:nw].copy())
+    return out
+
+
+def _words_batch(word_streams, done=True):
+    keep = [np.ascontiguousarray(s, dtype=np.uint32) for s in word_streams]
+    b = CseWords()
+    for i, a in enumerate(keep):
+        b.count[i] = a.shape[0]
+        if a.shape[0]:
+            b.words[i] = C.cast(a.ctypes.data, C.POINTER(C.c_uint32))
+    b.done = 1 if done else 0
+    return b, keep
+
+
+def encode_archive_words(Cvals, word_streams, n: int, offset: int, cfg: bytes | None = None, threads: int = 1) -> bytes:
+    """Archive writer over BCE_EMIT_CODER word streams."""
+    lib = load_library()
+    Cv = (C.c_uint32 * 8)(*Cvals)
+    cfgbuf = np.frombuffer(cfg, dtype=np.uint8) if cfg is not None else None
+    w = lib.bce_archive_begin(n, Cv, cfgbuf.ctypes.data if cfgbuf is not None else None)
+    b, keep = _words_batch(word_streams)
+    assert lib.bce_archive_feed_words(w, C.byref(b), threads) == 0
+    words = C.c_void_p()
+    nw = C.c_size_t()
+    rc = lib.bce_archive_finish(w, offset, C.byref(words), C.byref(nw))
+    if rc != 0:
+        raise RuntimeError(f"bce_archive_finish failed: {rc}")
+    out = C.string_at(words.value, nw.value * 2)
+    lib.bce_host_free(words)
+    return out
+
+
+def scan_config_words(word_streams) -> bytes:
+    lib = load_library()
+    s = lib.bce_scan_begin()
+    b, keep = _words_batch(word_streams)
+    lib.bce_scan_feed_words(s, C.byref(b))
+    out = np.zeros(288, dtype=np.uint8)
+    rc = lib.bce_scan_finish(s, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"bce_scan_finish failed: {rc}")
+    return out.tobytes()
 
 
 def scan_config(streams) -> bytes:

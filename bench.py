@@ -176,7 +176,8 @@ def run_reference(args, rank: int, world: int):
 def algorithmic_bytes(st: dict) -> dict:
     n = st["n"]
     stage_a = 19 * n + sum((44 + 24 * p) * m for m, p in zip(st["sort_m"], st["sort_passes"]))
-    stage_b = 19 * n + 48 * st["cse_visits"] + 20 * st["cse_tuples"]
+    # emission counted at the bytes actually written: 4 B per packed word (SURVEY.md 8d assumes 20 B raw counts)
+    stage_b = 19 * n + 48 * st["cse_visits"] + 4 * st["cse_words"]
     return {"stage_a": stage_a, "stage_b": stage_b, "total": stage_a + stage_b}
 
 
@@ -214,6 +215,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         return float(t.item())
 
     # ---- value leg: device resident ----------------------------------------------------------
+    from bce_b200.gpu import EMIT_CODER
+    fe.set_emit_mode(EMIT_CODER)          # what `bce -c` consumes: coder-ready 4-byte words
     fe.stage_input(host_in)
     for _ in range(args.warmup):
         fe.front_resident()
@@ -260,9 +263,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         k_ms = radix_ms / k_launches
         note = "sum of CUDA-event pairs around every radix_onesweep_kernel launch of the step"
     else:
-        k_name = "cse_rounds_kernel"
+        k_name = "cse_wide_kernel + cse_narrow_kernel (level loop)"
         k_launches = max(1, st["cse_launches"])
-        k_bytes = (48.0 * st["cse_visits"] + 20.0 * st["cse_tuples"]) / k_launches
+        k_bytes = (48.0 * st["cse_visits"] + 4.0 * st["cse_words"]) / k_launches
         k_ms = cse_ms / k_launches
         note = "one launch runs all rounds of the level loop"
     achieved = k_bytes / (k_ms / 1e3) / 1e9
@@ -273,7 +276,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                "frac": ab["total"] / (st["ms_total"] / 1e3) / 1e9 / peak,
                                "stage_a_bytes": ab["stage_a"], "stage_b_bytes": ab["stage_b"]}}
 
-    gathered = batch.gather_stats(batch.RankStats(args.steps, nbytes * args.steps, 0, st["cse_tuples"], dev_ms, wall_ms),
+    gathered = batch.gather_stats(batch.RankStats(args.steps, nbytes * args.steps, 0, st["cse_words"], dev_ms, wall_ms),
                                   device="cuda" if world > 1 else "cpu")
 
     # ---- cpu baseline (rank 0, N = 1 only) ---------------------------------------------------------
@@ -305,12 +308,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "stage_ms": {k: st[k] for k in ("ms_pack", "ms_radix", "ms_rerank", "ms_rekey", "ms_bwt_gather",
                                             "ms_wavelet", "ms_cse", "ms_bwt_total", "ms_cse_total")},
             "counters": {"sort_rounds": st["sort_rounds"], "sort_m": st["sort_m"], "sort_passes": st["sort_passes"],
-                         "visits": st["cse_visits"], "counts": st["cse_tuples"], "cse_rounds": st["cse_rounds"],
+                         "visits": st["cse_visits"], "emitted_words": st["cse_words"], "cse_rounds": st["cse_rounds"],
                          "peak_frontier": st["cse_peak_frontier"]},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes,
-                    "d2h_bytes_per_step": int(counts) * 20 + 64, "ms_per_step": e2e_ms / args.steps,
+                    "d2h_bytes_per_step": int(counts) * 4 + 64, "emission": "BCE_EMIT_CODER packed words", "ms_per_step": e2e_ms / args.steps,
                     "ms_h2d": st_e2e["ms_h2d"], "ms_d2h": st_e2e["ms_d2h"]},
             "gpu_launches": int(sum(s["gpu_launches"] for s in stats_list)),
             "clocks": clocks,

@@ -79,6 +79,7 @@ typedef struct bce_gpu_stats {
   float ms_cse_narrow;           /* part of ms_cse spent in the narrow-frontier (cluster) kernel */
   uint32_t cse_rounds_narrow;    /* rounds run by it */
   float ms_radix_kernel;         /* sum over launches of radix_onesweep_kernel alone (event pairs) */
+  uint64_t cse_words;            /* 32-bit words emitted (5 per count raw, 1-2 packed) */
 } bce_gpu_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------- */
@@ -117,6 +118,26 @@ int bce_gpu_wavelet(bce_gpu_ctx *ctx, const uint8_t *L, uint32_t n,
  * cse_next runs rounds on the device and hands back the next batch of emitted counts. */
 int bce_gpu_cse_begin(bce_gpu_ctx *ctx, const uint8_t *L, uint32_t n, uint32_t C_out[8]);
 int bce_gpu_cse_next(bce_gpu_ctx *ctx, bce_cse_batch *out);
+
+/* ---- packed emission (what `bce -c` / `bce -s` of this repository use) ----------------
+ * Instead of the five raw arguments (20 B) the device can emit what the host coder consumes:
+ *   BCE_EMIT_CODER  one word  [0|nb=0|ctx:10 @10|k:5 @5|sym:5]  with ctx = the context index of
+ *                   AdaptiveCoder::get_context (bce.cpp:671-677) for the stream's configured
+ *                   context bits cfg288[stream][k]; when the reference would halve k > 31
+ *                   (bce.cpp:507-510) nb times: [1|nb:5 @20|ctx|k'|sym'] followed by one word
+ *                   with the nb low bits of the symbol (coded uniformly, LSB first)
+ *   BCE_EMIT_SCAN   one word  [esc|nb:5 @26|q2:8 @18|q1:8 @10|k:5 @5|sym:5], q = (c << 8) / cs,
+ *                   halving rule of ScanCoder::set (bce.cpp:737-744)
+ * set_emit_mode applies to the following cse_begin / compress_front calls of the context.
+ * cfg288: 9 x 32 context-bit table (rows 0..7 are used), NULL = default table. */
+enum { BCE_EMIT_RAW = 0, BCE_EMIT_CODER = 1, BCE_EMIT_SCAN = 2 };
+typedef struct bce_cse_words {
+  const uint32_t *words[8];   /* pinned host memory, valid until the next cse_next* call */
+  size_t count[8];            /* words */
+  int done;
+} bce_cse_words;
+int bce_gpu_set_emit_mode(bce_gpu_ctx *ctx, int mode, const uint8_t *cfg288);
+int bce_gpu_cse_next_words(bce_gpu_ctx *ctx, bce_cse_words *out);
 
 /* ---- fused front end -------------------------------------------------------------
  * bce_gpu_bwt + bce_gpu_cse_begin without the BWT leaving the device: what

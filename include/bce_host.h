@@ -26,6 +26,8 @@ bce_archive_writer *bce_archive_begin(uint32_t n, const uint32_t C[8], const uin
 /* feed one batch (all 8 streams); threads > 1 codes the streams concurrently (one thread per
  * stream at most, like the reference's omp parallel for over the 8 levels, bce.cpp:1250). */
 int bce_archive_feed(bce_archive_writer *w, const bce_cse_batch *batch, int threads);
+/* same for BCE_EMIT_CODER word batches (the config must be the one given to bce_gpu_set_emit_mode) */
+int bce_archive_feed_words(bce_archive_writer *w, const bce_cse_words *batch, int threads);
 /* flush, header (n, offset, sizes), concatenate; *words is malloc'd (bce_host_free). */
 int bce_archive_finish(bce_archive_writer *w, uint32_t offset, uint16_t **words, size_t *nwords);
 void bce_archive_abort(bce_archive_writer *w);
@@ -35,12 +37,18 @@ void bce_archive_abort(bce_archive_writer *w);
 typedef struct bce_scan bce_scan;
 bce_scan *bce_scan_begin(void);
 int bce_scan_feed(bce_scan *s, const bce_cse_batch *batch);
+int bce_scan_feed_words(bce_scan *s, const bce_cse_words *batch);   /* BCE_EMIT_SCAN batches */
 int bce_scan_finish(bce_scan *s, uint8_t cfg288_out[288]);
 
 /* whole pipelines over a memory buffer, GPU front end + host coders */
 int bce_compress_buffer(bce_gpu_ctx *ctx, const uint8_t *T, uint32_t n, const uint8_t *cfg288,
                         int threads, uint16_t **words, size_t *nwords);
 int bce_scan_buffer(bce_gpu_ctx *ctx, const uint8_t *T, uint32_t n, uint8_t cfg288_out[288]);
+
+/* host-side packer with the device's word formats (mode = BCE_EMIT_CODER / BCE_EMIT_SCAN);
+ * words must hold 2 * count entries; returns the number of words written */
+size_t bce_host_pack_counts(int mode, const uint8_t *cfg288, int stream, const bce_tuple *t, size_t count,
+                            uint32_t *words);
 
 const uint8_t *bce_host_default_config(void);   /* 288 bytes */
 void bce_host_free(void *p);

@@ -102,3 +102,31 @@ def test_resident_matches_hosted(frontend):
     frontend.stage_input(data)
     off2, tuples = frontend.front_resident()
     assert off2 == off and tuples == sum(s.shape[0] for s in streams)
+
+
+PACKED = [c for c in CASES if c[0] in ("kat-hello", "kat-run", "bytes-256", "long-repeat", "markov2-200k", "mixed-2MiB+5")]
+
+
+@pytest.mark.parametrize("name,data,primitive", PACKED, ids=[c[0] for c in PACKED])
+def test_packed_emission_matches_host_packer(frontend, name, data, primitive):
+    """BCE_EMIT_CODER / BCE_EMIT_SCAN words from the device == the host packer applied to the
+    oracle's raw counts, word for word."""
+    from bce_b200 import host
+    from bce_b200.gpu import EMIT_CODER, EMIT_SCAN
+    Lo, offo, _ = oracle.bwt(data)
+    want = oracle.cse(oracle.wavelet(Lo), len(data))
+    for mode in (EMIT_CODER, EMIT_SCAN):
+        off, Cv, words = frontend.compress_front_words(data, mode)
+        ref = host.pack_counts(mode, want["streams"])
+        assert off == offo and Cv == want["C"]
+        for i in range(8):
+            assert first_diff(words[i], ref[i]) is None, (mode, i, first_diff(words[i], ref[i]))
+
+
+@pytest.mark.parametrize("name,data,primitive", PACKED, ids=[c[0] for c in PACKED])
+def test_compress_and_scan_pipelines(frontend, name, data, primitive):
+    """bce -c / bce -s of this repository: GPU front end (packed words) + host coders."""
+    from bce_b200 import host
+    assert host.compress(frontend, data, threads=8) == oracle.compress(data)
+    want = oracle.cse(oracle.wavelet(oracle.bwt(data)[0]), len(data))
+    assert host.scan(frontend, data) == host.scan_config(want["streams"])

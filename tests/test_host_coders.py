@@ -67,3 +67,42 @@ def test_wide_ranges_take_the_binary_decomposition():
         streams.append(np.stack([s, k, c1, c2, cs], axis=1).astype(np.uint32))
     Cv = [5] * 8
     assert host.encode_archive(Cv, streams, 1000, 3) == oracle.encode_archive(Cv, streams, 1000, 3)
+
+
+def test_packed_words_give_the_same_archive_and_config():
+    """The device's packed formats (include/bce_gpu.h), produced here by the host packer from
+    the oracle's raw counts, must code to the same archive / scan config as the raw counts."""
+    from bce_b200.gpu import EMIT_CODER, EMIT_SCAN
+    g = json.loads((GOLD / "scan_markov2_200k.json").read_text())
+    cases = dict((c[0], c[1]) for c in small_cases() + medium_cases())
+    for name in ("kat-hello", "kat-run", "bytes-256", "markov2-200k", "long-repeat"):
+        data = cases[name]
+        off, c = streams_of(data)
+        words = host.pack_counts(EMIT_CODER, c["streams"])
+        assert sum(w.size for w in words) >= sum(s.shape[0] for s in c["streams"])
+        assert host.encode_archive_words(c["C"], words, len(data), off, threads=8) == oracle.compress(data), name
+    data = cases[g["input"]]
+    off, c = streams_of(data)
+    cfg = bytes.fromhex(g["config_hex"])
+    assert host.scan_config_words(host.pack_counts(EMIT_SCAN, c["streams"])) == cfg
+    words = host.pack_counts(EMIT_CODER, c["streams"], cfg=cfg)
+    arc = host.encode_archive_words(c["C"], words, len(data), off, cfg=cfg)
+    assert hashlib.sha256(arc).hexdigest() == g["archive_with_config_sha256"]
+
+
+def test_packed_wide_ranges():
+    """k > 31 (escape word + low bits) and uint32 wrap of the context index."""
+    import numpy as np
+    from bce_b200.gpu import EMIT_CODER
+    rng = np.random.default_rng(5)
+    streams = []
+    for i in range(8):
+        k = rng.integers(2, 1 << 20, size=300, dtype=np.uint32)
+        s = (rng.integers(0, 1 << 30, size=300, dtype=np.uint32) % k).astype(np.uint32)
+        cs = rng.integers(2, 1 << 31, size=300, dtype=np.uint32)
+        c1 = (rng.integers(0, 1 << 31, size=300, dtype=np.uint32) % cs).astype(np.uint32)
+        c2 = (rng.integers(0, 1 << 31, size=300, dtype=np.uint32) % cs).astype(np.uint32)
+        streams.append(np.stack([s, k, c1, c2, cs], axis=1).astype(np.uint32))
+    Cv = [7] * 8
+    words = host.pack_counts(EMIT_CODER, streams)
+    assert host.encode_archive_words(Cv, words, 2000, 11) == oracle.encode_archive(Cv, streams, 2000, 11)

@@ -17,6 +17,8 @@
 //
 // Kernels: K1 pack, K2 radix pass (radix_sort.cu), K3 re-rank + stable compaction
 // (single pass, chained scan), K4 key rebuild (gather-bound), K5 BWT gather (gather-bound).
+#include <stdlib.h>
+
 #include "ctx.h"
 
 namespace bce {
@@ -85,6 +87,7 @@ struct RerankArgs {
   uint32_t* ticket;
   uint32_t tag;
   uint32_t* err;
+  uint32_t dbg;             // timing experiments only: 1 no rank scatter, 2 no SA write, 4 no compaction writes
 };
 
 __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
@@ -185,9 +188,9 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
     if (shead_bits >> j & 1u) ++gd_run;
     // slots of one group are consecutive in SA, so the head's SA position is sap - distance
     uint32_t rank = sap[j] - (q - (cur_head - 1));
-    a.sa[sap[j]] = idx[j];
-    a.rnk[idx[j]] = rank;
-    if (surv_bits >> j & 1u) {
+    if (!(a.dbg & 2u)) a.sa[sap[j]] = idx[j];
+    if (!(a.dbg & 1u)) a.rnk[idx[j]] = rank;
+    if ((surv_bits >> j & 1u) && !(a.dbg & 4u)) {
       a.idx_out[out_at] = idx[j];
       a.sapos_out[out_at] = sap[j];
       a.gd_out[out_at] = gd_run - 1;
@@ -353,13 +356,17 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     a.ticket = d_ticket;
     a.tag = uint32_t(next_tag(c));
     a.err = d_err;
+    { const char* v = getenv("BCE_GPU_RERANK_DBG"); a.dbg = v ? uint32_t(atoi(v)) : 0u; }
     BCE_CUDA(c, cudaMemsetAsync(d_ticket, 0, 4, st));
     rerank_kernel<<<a.tiles, RR_THREADS, 0, st>>>(a);
     S.gpu_launches++;
     BCE_CUDA(c, cudaGetLastError());
     BCE_CUDA(c, cudaMemcpyAsync(h_small, d_totals, 8, cudaMemcpyDeviceToHost, st));
     BCE_CUDA(c, cudaMemcpyAsync(h_small + 2, d_err, 4, cudaMemcpyDeviceToHost, st));
-    BCE_TRY(lap(S.ms_rerank));      // synchronises
+    { const float before = S.ms_rerank;
+      BCE_TRY(lap(S.ms_rerank));      // synchronises
+      BCE_TRACE("rerank round %d m=%u: %.3f ms (dbg=%u)", round, m, S.ms_rerank - before, a.dbg);
+      if (a.dbg) { set_error(c, "rerank timing experiment"); return BCE_GPU_E_INTERNAL; } }
     if (h_small[2]) { set_error(c, "suffix sort: chained-scan watchdog fired"); return BCE_GPU_E_INTERNAL; }
     uint32_t m_next = h_small[0];
     groups = h_small[1];

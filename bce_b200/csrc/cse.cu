@@ -443,6 +443,7 @@ int cse_begin(Ctx* c, uint32_t n) {
   H->last_round = 0;
   H->known_nodes = 0;
   H->pending = H->pending_done = H->finished = false;
+  H->pinned_flip = 0;                        // single-batch runs always land in the same pinned buffer
   const int items = int(env_size("BCE_GPU_CSE_ITEMS", 0));
   H->fixed_items = (items == 2 || items == 4) ? items : 0;
 

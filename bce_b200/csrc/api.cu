@@ -260,7 +260,7 @@ void bce_gpu_close(bce_gpu_ctx* h) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   bce::cse_destroy(c);
   c->text.release(); c->bwt.release(); c->ranks.release(); c->scratch.release();
-  c->small.release(); c->desc.release();
+  c->small.release(); c->desc.release(); c->radix_tmp.release();
   c->pinned_small.release(); c->pinned_emit.release(); c->pinned_io.release();
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->pass_ev) if (e) cudaEventDestroy(e);

@@ -30,6 +30,7 @@ struct Ctx : bce_gpu_ctx {
   DevBuf scratch;     // carved per stage
   DevBuf small;       // counters, histograms, descriptors' tickets, state structs
   DevBuf desc;        // tile descriptors (tagged, never cleared between passes)
+  DevBuf radix_tmp;   // per-chunk digit histograms / offsets of the chunked radix pass
   PinnedBuf pinned_small;   // host mirror for small read-backs
   PinnedBuf pinned_emit;    // emitted counts handed to the caller (two buffers alternate)
   PinnedBuf pinned_emit2;

@@ -9,6 +9,8 @@
 // Digit histograms for all passes of one sort come from one extra read of the keys.
 //
 // HBM traffic per pass: read 12 B + write 12 B per element  (24 m P_r).
+#include <stdlib.h>
+
 #include "ctx.h"
 
 namespace bce {
@@ -140,6 +142,12 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(RadixPass p)
   }
 }
 
+}  // namespace bce
+
+#include "radix_chunked.cuh"
+
+namespace bce {
+
 static uint32_t g_radix_dbg = 0;
 
 int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uint32_t* valB,
@@ -189,6 +197,24 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
   uint64_t* kin = keyA; uint64_t* kout = keyB;
   uint32_t* vin = valA; uint32_t* vout = valB;
   const uint32_t tiles = (m + RS_TILE - 1) / RS_TILE;
+  // single-pass onesweep kernel (default) or chunked reduce/scan/scatter (BCE_GPU_RADIX=chunked):
+  // measured on B200 the chunked variant is the slower one (100 M random pairs, 8 passes:
+  // 16.1 ms against 9.9 ms), see profiles/r1_radix_experiments.md
+  const char* which = getenv("BCE_GPU_RADIX");
+  const bool chunked = which && which[0] == 'c';
+  uint32_t chunk = 0, chunks = 0;
+  uint32_t* d_chist = nullptr;
+  uint32_t* d_offs = nullptr;
+  if (chunked) {
+    const uint32_t ctas = uint32_t(c->sm_count) * 3;                      // 3 resident CTAs per SM
+    const uint32_t dtiles = (m + RD_TILE - 1) / RD_TILE;
+    const uint32_t per = (dtiles + ctas - 1) / ctas;                      // tiles per chunk
+    chunk = per * RD_TILE;
+    chunks = (m + chunk - 1) / chunk;
+    BCE_TRY(c->radix_tmp.ensure(c, size_t(chunks) * 256 * 4 * 2));
+    d_chist = c->radix_tmp.as<uint32_t>();
+    d_offs = d_chist + size_t(chunks) * 256;
+  }
   int ran = 0;
   for (int p = 0; p < npass; ++p) {
     if (!run[p]) continue;
@@ -203,7 +229,17 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
     a.dbg = g_radix_dbg;
     const bool timed = c->pass_ev_n + 2 <= 256;
     if (timed) cudaEventRecord(c->pass_ev[c->pass_ev_n], c->stream);
-    radix_onesweep_kernel<<<tiles, RS_THREADS, 0, c->stream>>>(a);
+    if (chunked) {
+      RadixDown dn;
+      dn.kin = kin; dn.vin = vin; dn.kout = kout; dn.vout = vout;
+      dn.m = m; dn.chunk = chunk; dn.shift = shifts[p]; dn.offs = d_offs;
+      radix_upsweep_kernel<<<chunks, RD_THREADS, 0, c->stream>>>(kin, m, chunk, shifts[p], d_chist);
+      radix_chunk_scan_kernel<<<1, 256, 0, c->stream>>>(d_chist, chunks, d_offs);
+      radix_downsweep_kernel<<<chunks, RD_THREADS, 0, c->stream>>>(dn);
+      c->stats.gpu_launches += 2;
+    } else {
+      radix_onesweep_kernel<<<tiles, RS_THREADS, 0, c->stream>>>(a);
+    }
     if (timed) { cudaEventRecord(c->pass_ev[c->pass_ev_n + 1], c->stream); c->pass_ev_n += 2; }
     c->stats.gpu_launches++;
     c->stats.radix_launches++;

@@ -84,8 +84,8 @@ def build_synth(force: bool = False) -> Path:
 
 
 def build_host(force: bool = False) -> Path:
-    srcs = [HOST / "coders.cpp", HOST / "archive.cpp", HOST / "host_api.cpp"]
-    hdrs = [HOST / "coders.hpp", HOST / "archive.hpp", ROOT / "include" / "bce_gpu.h", ROOT / "include" / "bce_host.h"]
+    srcs = [HOST / "coders.cpp", HOST / "archive.cpp", HOST / "decode.cpp", HOST / "host_api.cpp"]
+    hdrs = [HOST / "coders.hpp", HOST / "archive.hpp", HOST / "decode.hpp", ROOT / "include" / "bce_gpu.h", ROOT / "include" / "bce_host.h"]
     if not all(s.exists() for s in srcs):
         return LIB_HOST
     if force or _stale(LIB_HOST, srcs + hdrs):
@@ -93,7 +93,7 @@ def build_host(force: bool = False) -> Path:
               "-L", PKG, "-lbce_gpu", "-Wl,-rpath,$ORIGIN"])
     main = HOST / "bce_main.cpp"
     if main.exists() and (force or _stale(BIN_BCE, srcs + hdrs + [main, LIB_GPU])):
-        _run([_cxx(), *HOST_FLAGS, "-o", BIN_BCE, main, *srcs, "-I", ROOT / "include",
+        _run([_cxx(), *HOST_FLAGS, "-DBCE_HAVE_DECODER", "-o", BIN_BCE, main, *srcs, "-I", ROOT / "include",
               "-L", PKG, "-lbce_gpu", "-Wl,-rpath,$ORIGIN", "-ldl"])
     return LIB_HOST
 

@@ -127,7 +127,11 @@ int main(int argc, char** argv) {
     }
     std::vector<uint8_t> out;
     const int rc = bcehost::decode_archive(words, argv[1][2] == 's', out);
-    if (rc) return rc;
+    if (rc) {
+      std::printf("Decoding failed: %s%s\n", bce_gpu_error_string(rc),
+                  argv[1][2] == 's' ? "" : " (bce -ds decodes without a GPU)");
+      return rc;
+    }
     const std::chrono::duration<double> d = clock::now() - start;
     std::printf("Decompressed from %zu B -> %zu B in %.1f s\n", size_t(size), out.size(), d.count());
     std::ofstream file(argv[2], std::ios::binary | std::ios::trunc);

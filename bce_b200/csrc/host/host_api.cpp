@@ -5,6 +5,7 @@
 
 #include "../../../include/bce_host.h"
 #include "archive.hpp"
+#include "decode.hpp"
 
 using namespace bcehost;
 
@@ -90,6 +91,20 @@ int bce_scan_finish(bce_scan* h, uint8_t cfg288_out[288]) {
   std::memcpy(cfg288_out, t.data(), 288);
   delete h->s;
   delete h;
+  return BCE_GPU_OK;
+}
+
+int bce_decode_buffer(const uint16_t* words, size_t nwords, int low_memory, uint8_t** out, size_t* nout) {
+  if (!words || !out || !nout) return BCE_GPU_E_ARG;
+  std::vector<uint16_t> archive(words, words + nwords);
+  std::vector<uint8_t> text;
+  const int rc = decode_archive(archive, low_memory != 0, text);                 // BCE::decode, bce.cpp:1169-1233
+  if (rc) return rc;
+  uint8_t* mem = static_cast<uint8_t*>(std::malloc(text.size() + 1));
+  if (!mem) return BCE_GPU_E_NOMEM;
+  std::memcpy(mem, text.data(), text.size());
+  *out = mem;
+  *nout = text.size();
   return BCE_GPU_OK;
 }
 

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(RadixPass p)
     uint32_t idx = wbase + k * 32 + lane;
     bool in = idx < p.m;
     key[k] = in ? p.kin[idx] : ~0ull;      // padding sorts to the very end of the tile
-    val[k] = in ? p.vin[idx] : 0u;
+    val[k] = (in && p.vin) ? p.vin[idx] : 0u;     // vin == NULL: keys only
   }
   // rank inside the warp's chunk, in index order (stable)
 #pragma unroll
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(RadixPass p)
     uint32_t d = uint32_t(k64 >> p.shift) & 255u;
     uint32_t g = s_goff[d] + j;
     p.kout[g] = k64;
-    p.vout[g] = s_vals[j];
+    if (p.vout) p.vout[g] = s_vals[j];
   }
 }
 

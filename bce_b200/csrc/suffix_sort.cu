@@ -19,6 +19,8 @@
 // (single pass, chained scan), K4 key rebuild (gather-bound), K5 BWT gather (gather-bound).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "ctx.h"
 
 namespace bce {
@@ -78,6 +80,7 @@ struct RerankArgs {
   uint32_t m;
   uint32_t* sa;
   uint32_t* rnk;
+  uint64_t* pairs;          // when set: (idx << 32 | rank) per slot instead of the random rank scatter
   uint32_t* idx_out;        // compacted working set of the next round
   uint32_t* sapos_out;
   uint32_t* gd_out;         // dense group id of every survivor
@@ -189,7 +192,8 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
     // slots of one group are consecutive in SA, so the head's SA position is sap - distance
     uint32_t rank = sap[j] - (q - (cur_head - 1));
     if (!(a.dbg & 2u)) a.sa[sap[j]] = idx[j];
-    if (!(a.dbg & 1u)) a.rnk[idx[j]] = rank;
+    if (a.pairs) a.pairs[q] = (uint64_t(idx[j]) << 32) | rank;
+    else if (!(a.dbg & 1u)) a.rnk[idx[j]] = rank;
     if ((surv_bits >> j & 1u) && !(a.dbg & 4u)) {
       a.idx_out[out_at] = idx[j];
       a.sapos_out[out_at] = sap[j];
@@ -201,6 +205,15 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
     a.totals[0] = s_carry[1] + uint32_t(tile_sum);
     a.totals[1] = s_carry[2] + uint32_t(tile_sum >> 32);
   }
+}
+
+// K3b: ranks from (idx, rank) pairs that were partitioned by the top bits of idx
+__global__ void __launch_bounds__(256) scatter_ranks_kernel(const uint64_t* __restrict__ pairs, uint32_t m,
+                                                            uint32_t* __restrict__ rnk) {
+  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  const uint64_t p = pairs[q];
+  rnk[uint32_t(p >> 32)] = uint32_t(p);
 }
 
 // ---------------------------------------------------------------------------------
@@ -348,6 +361,14 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     RerankArgs a;
     a.key = ks; a.idx = vs; a.sapos = sap_cur; a.m = m;
     a.sa = sa; a.rnk = rnk;
+    // Large working sets: a billion random 4-byte stores into a 4n-byte array cost more than
+    // everything else in this kernel together (each one a read-modify-write of a 32-byte
+    // sector).  Write (idx, rank) pairs in slot order instead, partition them by the top 8 bits
+    // of idx with one keys-only radix pass, and scatter from that order: every 1/256 slice of
+    // the rank array then stays in L2 while it is being filled.
+    const bool partitioned = !getenv("BCE_GPU_NO_PARTITION") && m >= (8u << 20) && size_t(n) * 4 > (size_t(64) << 20);
+    uint64_t* pair_buf = (ks == keyA) ? keyB : keyA;
+    a.pairs = partitioned ? pair_buf : nullptr;
     a.idx_out = v_other; a.sapos_out = sap_next; a.gd_out = gd_next;
     a.totals = d_totals;
     a.tiles = (m + RR_TILE - 1) / RR_TILE;
@@ -365,8 +386,19 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     BCE_CUDA(c, cudaMemcpyAsync(h_small + 2, d_err, 4, cudaMemcpyDeviceToHost, st));
     { const float before = S.ms_rerank;
       BCE_TRY(lap(S.ms_rerank));      // synchronises
-      BCE_TRACE("rerank round %d m=%u: %.3f ms (dbg=%u)", round, m, S.ms_rerank - before, a.dbg);
+      BCE_TRACE("rerank round %d m=%u: %.3f ms (dbg=%u, partitioned=%d)", round, m, S.ms_rerank - before, a.dbg, int(partitioned));
       if (a.dbg) { set_error(c, "rerank timing experiment"); return BCE_GPU_E_INTERNAL; } }
+    if (partitioned) {
+      const int pshift = 32 + std::max(0, nbits - 8);
+      uint64_t* pk; uint32_t* pv; int pran = 0;
+      BCE_TRY(radix_sort_pairs(c, pair_buf, ks, nullptr, nullptr, m, &pshift, 1, &pk, &pv, &pran));
+      scatter_ranks_kernel<<<(m + 255) / 256, 256, 0, st>>>(pk, m, rnk);
+      S.gpu_launches++;
+      BCE_CUDA(c, cudaGetLastError());
+      const float before = S.ms_rerank;
+      BCE_TRY(lap(S.ms_rerank));
+      BCE_TRACE("rank partition + scatter: %.3f ms", S.ms_rerank - before);
+    }
     if (h_small[2]) { set_error(c, "suffix sort: chained-scan watchdog fired"); return BCE_GPU_E_INTERNAL; }
     uint32_t m_next = h_small[0];
     groups = h_small[1];

@@ -15,7 +15,7 @@ HOST_SYMBOLS = [
     "bce_archive_begin", "bce_archive_feed", "bce_archive_finish", "bce_archive_abort",
     "bce_scan_begin", "bce_scan_feed", "bce_scan_finish", "bce_compress_buffer", "bce_scan_buffer",
     "bce_host_default_config", "bce_host_free",
-    "bce_archive_feed_words", "bce_scan_feed_words", "bce_host_pack_counts",
+    "bce_archive_feed_words", "bce_scan_feed_words", "bce_host_pack_counts", "bce_decode_buffer",
 ]
 
 
@@ -42,6 +42,7 @@ def load_library() -> C.CDLL:
         lib.bce_scan_feed_words.argtypes = [vp, C.POINTER(CseWords)]
         lib.bce_host_pack_counts.argtypes = [C.c_int, vp, C.c_int, vp, C.c_size_t, vp]
         lib.bce_host_pack_counts.restype = C.c_size_t
+        lib.bce_decode_buffer.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]
         _lib = lib
     return _lib
 
@@ -146,6 +147,20 @@ def scan_config(streams) -> bytes:
     if rc != 0:
         raise RuntimeError(f"bce_scan_finish failed: {rc}")
     return out.tobytes()
+
+
+def decompress(archive: bytes, low_memory: bool = False) -> bytes:
+    """`bce -d` (GPU inverse BWT) / `bce -ds` (serial, host only) on an archive in memory."""
+    lib = load_library()
+    a = np.frombuffer(archive, dtype=np.uint16)
+    out = C.c_void_p()
+    n = C.c_size_t()
+    rc = lib.bce_decode_buffer(a.ctypes.data, a.size, 1 if low_memory else 0, C.byref(out), C.byref(n))
+    if rc != 0:
+        raise RuntimeError(f"bce_decode_buffer failed: {rc}")
+    data = C.string_at(out.value, n.value)
+    lib.bce_host_free(out)
+    return data
 
 
 def default_config() -> bytes:

@@ -50,6 +50,11 @@ int bce_scan_buffer(bce_gpu_ctx *ctx, const uint8_t *T, uint32_t n, uint8_t cfg2
 size_t bce_host_pack_counts(int mode, const uint8_t *cfg288, int stream, const bce_tuple *t, size_t count,
                             uint32_t *words);
 
+/* `bce -d` (low_memory = 0: inverse BWT on the GPU through bce_gpu_unbwt) and `bce -ds`
+ * (low_memory = 1: serial unbwt::bitwise on the host, no GPU needed) over an archive in memory.
+ * *out is malloc'd (bce_host_free). */
+int bce_decode_buffer(const uint16_t *words, size_t nwords, int low_memory, uint8_t **out, size_t *nout);
+
 const uint8_t *bce_host_default_config(void);   /* 288 bytes */
 void bce_host_free(void *p);
 

@@ -130,3 +130,12 @@ def test_compress_and_scan_pipelines(frontend, name, data, primitive):
     assert host.compress(frontend, data, threads=8) == oracle.compress(data)
     want = oracle.cse(oracle.wavelet(oracle.bwt(data)[0]), len(data))
     assert host.scan(frontend, data) == host.scan_config(want["streams"])
+
+
+@pytest.mark.parametrize("name,data,primitive", [c for c in CASES if c[2]], ids=[c[0] for c in CASES if c[2]])
+def test_decompress_with_gpu_inverse(frontend, name, data, primitive):
+    """`bce -d`: host decoder + bce_gpu_unbwt, on archives written by this repository's bce -c path."""
+    from bce_b200 import host
+    arc = host.compress(frontend, data, threads=4)
+    assert arc == oracle.compress(data)
+    assert host.decompress(arc) == data

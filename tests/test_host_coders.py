@@ -106,3 +106,19 @@ def test_packed_wide_ranges():
     Cv = [7] * 8
     words = host.pack_counts(EMIT_CODER, streams)
     assert host.encode_archive_words(Cv, words, 2000, 11) == oracle.encode_archive(Cv, streams, 2000, 11)
+
+
+@pytest.mark.parametrize("name,data,primitive", [c for c in CASES if c[2]], ids=[c[0] for c in CASES if c[2]])
+def test_host_decoder_low_memory_path(name, data, primitive):
+    """`bce -ds`: header + 8 adaptive decoders + the level loop in decode mode + serial inverse,
+    all host code (csrc/host/decode.cpp); archives come from the oracle (= the reference's)."""
+    arc = oracle.compress(data)
+    assert host.decompress(arc, low_memory=True) == data
+    if oracle.have_ref() and len(data) <= 50000:
+        assert oracle.ref_decompress(arc, low_mem=True) == data
+
+
+def test_host_decoder_rejects_truncated_archives():
+    arc = oracle.compress(b"hello world, hello world! the quick brown fox jumps over the lazy dog")
+    with pytest.raises(RuntimeError):
+        host.decompress(arc[:2], low_memory=True)

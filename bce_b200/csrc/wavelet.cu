@@ -102,7 +102,10 @@ __global__ void __launch_bounds__(WV_THREADS) wavelet_pass_kernel(WaveletPass p)
 
   uint32_t tile_zeros;
   const uint32_t z_before_local = block_exclusive_scan<uint32_t, WV_THREADS>(n0, s_scan, tile_zeros);
-  if (tid == 0) s_carry = lookback_serial(p.desc, 1u, tile, p.tag, tile_zeros, p.err);
+  if (tid < 32) {                        // warp-wide chained scan (a single thread made every tile wait, see profiles/)
+    const uint32_t pre = lookback_warp_wide<4>(p.desc, tile, 0u, p.tag, tile_zeros, p.err);
+    if (tid == 0) s_carry = pre;
+  }
   __syncthreads();
   const uint32_t z_before = s_carry + z_before_local;       // zeros in [0, pos0)
   const uint32_t o_before = pos0 - z_before;                // ones  in [0, pos0)   (pos0 <= n here or unused)

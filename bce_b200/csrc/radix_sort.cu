@@ -15,15 +15,12 @@
 
 namespace bce {
 
-constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 12;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
-constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_MIN_TILE = 2048;       // smallest tile of any kernel configuration (descriptor sizing)
 constexpr int RS_MAX_PASSES = 8;
 
 struct RadixShifts { int s[RS_MAX_PASSES]; };
 
-size_t radix_desc_words(uint32_t m) { return (size_t(m) / RS_TILE + 1) * 256; }
+size_t radix_desc_words(uint32_t m) { return (size_t(m) / RS_MIN_TILE + 1) * 256; }
 
 // ---- histograms of every digit position in one read ------------------------------
 __global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t* __restrict__ keys, uint32_t m,
@@ -60,10 +57,14 @@ struct RadixPass {
   uint32_t dbg;           // timing experiments only: 1 = skip the chained scan (output order wrong)
 };
 
-__global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(RadixPass p) {
-  __shared__ uint64_t s_keys[RS_TILE];
-  __shared__ uint32_t s_vals[RS_TILE];
-  __shared__ uint32_t s_whist[RS_WARPS][256];
+template <int RS_THREADS, int RS_ITEMS, int MIN_CTAS>
+__global__ void __launch_bounds__(RS_THREADS, MIN_CTAS) radix_onesweep_kernel(RadixPass p) {
+  constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+  constexpr int RS_WARPS = RS_THREADS / 32;
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(rs_smem);                         // [RS_TILE]
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(rs_smem + size_t(RS_TILE) * 8);    // [RS_TILE]
+  uint32_t (*s_whist)[256] = reinterpret_cast<uint32_t (*)[256]>(rs_smem + size_t(RS_TILE) * 12);   // [RS_WARPS][256]
   __shared__ uint32_t s_goff[256];
   __shared__ uint32_t s_dstart[256];
   __shared__ uint32_t s_scan[RS_WARPS];
@@ -110,18 +111,22 @@ __global__ void __launch_bounds__(RS_THREADS) radix_onesweep_kernel(RadixPass p)
   {
     const uint32_t d = tid;
     uint32_t sum = 0;
+    if (d < 256u) {
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
       uint32_t c = s_whist[w][d];
       s_whist[w][d] = sum;
       sum += c;
     }
+    }
     uint32_t tot;
     uint32_t dstart = block_exclusive_scan<uint32_t, RS_THREADS>(sum, s_scan, tot);
-    s_dstart[d] = dstart;
-    uint32_t publish = (d == 255u) ? sum - (uint32_t(RS_TILE) - valid) : sum;
-    uint32_t excl = (p.dbg & 1u) ? tile * (publish ? 1u : 0u) : lookback_serial(p.desc + d, 256u, tile, p.tag, publish, p.err);
-    s_goff[d] = p.base[d] + excl - dstart;     // global index = s_goff[digit] + local index
+    if (d < 256u) {
+      s_dstart[d] = dstart;
+      uint32_t publish = (d == 255u) ? sum - (uint32_t(RS_TILE) - valid) : sum;
+      uint32_t excl = (p.dbg & 1u) ? tile * (publish ? 1u : 0u) : lookback_serial(p.desc + d, 256u, tile, p.tag, publish, p.err);
+      s_goff[d] = p.base[d] + excl - dstart;     // global index = s_goff[digit] + local index
+    }
   }
   __syncthreads();
 
@@ -196,6 +201,27 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
 
   uint64_t* kin = keyA; uint64_t* kout = keyB;
   uint32_t* vin = valA; uint32_t* vout = valB;
+  // kernel configuration (threads x keys per thread); BCE_GPU_RADIX_CFG picks one for experiments
+  struct Cfg { void (*fn)(RadixPass); int threads, items; };
+  static const Cfg cfgs[] = {
+    {radix_onesweep_kernel<256, 12, 3>, 256, 12},
+    {radix_onesweep_kernel<256, 16, 3>, 256, 16},
+    {radix_onesweep_kernel<512, 8, 2>, 512, 8},
+    {radix_onesweep_kernel<384, 12, 2>, 384, 12},
+    {radix_onesweep_kernel<256, 8, 4>, 256, 8},
+    {radix_onesweep_kernel<512, 12, 1>, 512, 12},
+  };
+  int which_cfg = 1;          // 256 x 16: fastest on B200 (400 MB text: 62.2 ms of radix kernels; 256 x 12: 66.2, 512 x 8: 75.2)
+  { const char* v = getenv("BCE_GPU_RADIX_CFG"); if (v && *v >= '0' && *v <= '5') which_cfg = *v - '0'; }
+  const Cfg& cfg = cfgs[which_cfg];
+  const int RS_TILE = cfg.threads * cfg.items;
+  const int RS_THREADS = cfg.threads;
+  const size_t rs_smem = size_t(RS_TILE) * 12 + size_t(cfg.threads / 32) * 1024;
+  static bool attr_set[6] = {};
+  if (!attr_set[which_cfg]) {
+    BCE_CUDA(c, cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem)));
+    attr_set[which_cfg] = true;
+  }
   const uint32_t tiles = (m + RS_TILE - 1) / RS_TILE;
   // single-pass onesweep kernel (default) or chunked reduce/scan/scatter (BCE_GPU_RADIX=chunked):
   // measured on B200 the chunked variant is the slower one (100 M random pairs, 8 passes:
@@ -238,7 +264,7 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
       radix_downsweep_kernel<<<chunks, RD_THREADS, 0, c->stream>>>(dn);
       c->stats.gpu_launches += 2;
     } else {
-      radix_onesweep_kernel<<<tiles, RS_THREADS, 0, c->stream>>>(a);
+      cfg.fn<<<tiles, RS_THREADS, rs_smem, c->stream>>>(a);
     }
     if (timed) { cudaEventRecord(c->pass_ev[c->pass_ev_n + 1], c->stream); c->pass_ev_n += 2; }
     c->stats.gpu_launches++;

@@ -314,7 +314,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes,
                     "d2h_bytes_per_step": int(counts) * 4 + 64, "emission": "BCE_EMIT_CODER packed words", "ms_per_step": e2e_ms / args.steps,
-                    "ms_h2d": st_e2e["ms_h2d"], "ms_d2h": st_e2e["ms_d2h"]},
+                    "ms_h2d": st_e2e["ms_h2d"], "ms_d2h": st_e2e["ms_d2h"],
+                    "ms_bwt_total": st_e2e["ms_bwt_total"], "ms_cse_total": st_e2e["ms_cse_total"],
+                    "cse_launches": st_e2e["cse_launches"]},
             "gpu_launches": int(sum(s["gpu_launches"] for s in stats_list)),
             "clocks": clocks,
             "per_rank": [vars(g) for g in gathered],

@@ -139,3 +139,23 @@ def test_decompress_with_gpu_inverse(frontend, name, data, primitive):
     arc = host.compress(frontend, data, threads=4)
     assert arc == oracle.compress(data)
     assert host.decompress(arc) == data
+
+
+def test_random_small_inputs_archive_parity(frontend):
+    """Property check over many seeded small inputs (sizes around the tile and word edges, tiny
+    and large alphabets, planted repeats): archive from the GPU front end == oracle archive."""
+    from bce_b200 import host
+    rng = np.random.default_rng(2024)
+    for trial in range(120):
+        n = int(rng.choice([1, 2, 3, 5, 8, 9, 31, 32, 33, 63, 64, 65, 255, 256, 257, 511, 1023, 1024, 1025,
+                            2047, 2049, 4095, 4096, 4097, 5000, 12289]))
+        sigma = int(rng.choice([1, 2, 3, 4, 16, 64, 256]))
+        data = rng.integers(0, sigma, size=n, dtype=np.uint8)
+        if n > 64 and trial % 3 == 0:                      # plant a long repeat
+            k = int(rng.integers(8, n // 2))
+            src = int(rng.integers(0, n - k))
+            dst = int(rng.integers(0, n - k))
+            data[dst:dst + k] = data[src:src + k].copy()
+        data = data.tobytes()
+        got = host.compress(frontend, data, threads=1)
+        assert got == oracle.compress(data), (trial, n, sigma)

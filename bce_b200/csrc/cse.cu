@@ -362,7 +362,8 @@ struct CseHost {
   // emission: one or two sets of device buffers (two = copy of batch k overlaps compute of k+1)
   int sets = 1;
   uint32_t* emit_dev[2][8] = {};
-  size_t ecap_words = 0;
+  size_t ecap_words = 0;                 // allocated per stream and set
+  size_t batch_words = 0;                // capacity the kernels are told (<= ecap_words); grows if a round does not fit
   int fill_set = 0;                      // set the kernels write next
   // a computed batch waiting to be copied out / returned
   bool pending = false, pending_done = false;
@@ -405,11 +406,12 @@ int cse_begin(Ctx* c, uint32_t n) {
   const size_t desc_bytes = Carver::need(3 * desc_tiles, 8);
   const size_t left = budget > frontier_bytes(cap) + desc_bytes ? budget - frontier_bytes(cap) - desc_bytes : 0;
   H->sets = (c->cse_resident || env_size("BCE_GPU_NO_OVERLAP", 0)) ? 1 : 2;
-  const size_t pinned_limit = env_size("BCE_GPU_PINNED_LIMIT", size_t(4) << 30);   // per pinned buffer (two are used)
+  // words handed back per batch and stream: small batches let the copy of batch k overlap the
+  // kernels of batch k+1 (two pinned buffers of this size alternate)
+  const size_t batch_bytes = env_size("BCE_GPU_PINNED_LIMIT", size_t(1) << 30);
   size_t ew = size_t(n) * wmax;                              // a level emits at most n-1 counts in total
   const size_t per_level_min = (cap + CS_MAX_TILE) * wmax;   // one round must always fit
   if (ew * 8 * 4 * H->sets > left) ew = left / (8 * 4 * H->sets);
-  if (!c->cse_resident && ew * 8 * 4 > pinned_limit) ew = pinned_limit / (8 * 4);
   if (ew < per_level_min) ew = per_level_min;
   const size_t need = frontier_bytes(cap) + desc_bytes + size_t(H->sets) * 8 * Carver::need(ew, 4) + 4096;
   BCE_TRY(c->scratch.ensure(c, need));
@@ -425,8 +427,9 @@ int cse_begin(Ctx* c, uint32_t n) {
     for (int l = 0; l < 8; ++l) H->emit_dev[s][l] = cv.take<uint32_t>(ew);
   if (!cv.ok()) { set_error(c, "cse_begin: scratch carve failed (need %zu)", need); return BCE_GPU_E_NOMEM; }
   H->ecap_words = ew;
+  H->batch_words = c->cse_resident ? ew : std::min(ew, std::max(batch_bytes / 32, size_t(1) << 16));
   H->fill_set = 0;
-  for (int l = 0; l < 8; ++l) { a.emit[l] = H->emit_dev[0][l]; a.ecap[l] = ew; }
+  for (int l = 0; l < 8; ++l) { a.emit[l] = H->emit_dev[0][l]; a.ecap[l] = H->batch_words; }
   const size_t words = size_t(n) / 32 + 1;
   for (int l = 0; l < 8; ++l) { a.ranks[l] = c->ranks.as<uint64_t>() + size_t(l) * words; a.C[l] = c->C[l]; }
   a.cap = uint32_t(cap);
@@ -452,17 +455,22 @@ int cse_begin(Ctx* c, uint32_t n) {
   c->stats.gpu_launches++;
   BCE_CUDA(c, cudaGetLastError());
 
-  if (!H->var_fn[0]) {
-    int p2 = 0, p4 = 0;
-    H->var_fn[0] = (const void*)cse_wide_kernel<2>; H->var_smem[0] = 2 * sizeof(WideStage<2>);
-    H->var_fn[1] = (const void*)cse_wide_kernel<4>; H->var_smem[1] = 2 * sizeof(WideStage<4>);
-    BCE_CUDA(c, cudaFuncSetAttribute(cse_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->var_smem[0])));
-    BCE_CUDA(c, cudaFuncSetAttribute(cse_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(H->var_smem[1])));
-    BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, cse_wide_kernel<2>, CS_THREADS, H->var_smem[0]));
-    BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p4, cse_wide_kernel<4>, CS_THREADS, H->var_smem[1]));
-    if (p2 < 1 || p4 < 1) { H->var_fn[0] = nullptr; set_error(c, "cse kernel does not fit on an SM"); return BCE_GPU_E_CUDA; }
-    H->var_grid[0] = p2 * c->sm_count;
-    H->var_grid[1] = p4 * c->sm_count;
+  {   // wide kernel instances: raw counts need 5 staging words per node, packed ones 2
+    const bool packed = a.emit_mode != kEmitRaw;
+    const void* f2 = packed ? (const void*)cse_wide_kernel<2, 2> : (const void*)cse_wide_kernel<2, 5>;
+    const void* f4 = packed ? (const void*)cse_wide_kernel<4, 2> : (const void*)cse_wide_kernel<4, 5>;
+    const size_t s2 = packed ? 2 * sizeof(WideStage<2, 2>) : 2 * sizeof(WideStage<2, 5>);
+    const size_t s4 = packed ? 2 * sizeof(WideStage<4, 2>) : 2 * sizeof(WideStage<4, 5>);
+    if (H->var_fn[0] != f2) {
+      int p2 = 0, p4 = 0;
+      BCE_CUDA(c, cudaFuncSetAttribute(f2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s2)));
+      BCE_CUDA(c, cudaFuncSetAttribute(f4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s4)));
+      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, f2, CS_THREADS, s2));
+      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p4, f4, CS_THREADS, s4));
+      if (p2 < 1 || p4 < 1) { H->var_fn[0] = nullptr; set_error(c, "cse kernel does not fit on an SM"); return BCE_GPU_E_CUDA; }
+      H->var_fn[0] = f2; H->var_smem[0] = s2; H->var_grid[0] = p2 * c->sm_count;
+      H->var_fn[1] = f4; H->var_smem[1] = s4; H->var_grid[1] = p4 * c->sm_count;
+    }
   }
   c->cse_active = true;
   c->cse_done = false;
@@ -561,6 +569,17 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
   size_t total = 0;
   for (int l = 0; l < 8; ++l) { cnt[l] = size_t(h_state->emitted[par][l]); total += cnt[l]; }
   if (h_state->status == kCseDrain && total == 0) {
+    // the coming round alone does not fit the batch size: enlarge it (the buffers are big enough
+    // for any round) and go on -- nothing was processed, no state is lost
+    if (H->batch_words < H->ecap_words) {
+      H->batch_words = std::min(H->ecap_words, H->batch_words * 2);
+      for (int l = 0; l < 8; ++l) H->args.ecap[l] = H->batch_words;
+      BCE_TRACE("cse: batch size raised to %zu words per stream", H->batch_words);
+      cse_reset_emitted_kernel<<<1, 32, 0, st>>>(H->args.st);
+      c->stats.gpu_launches++;
+      BCE_CUDA(c, cudaGetLastError());
+      return run_batch(c, set, cnt, done);
+    }
     set_error(c, "cse: kernel asked to drain empty emission buffers at round %u", h_state->round);
     return BCE_GPU_E_INTERNAL;
   }

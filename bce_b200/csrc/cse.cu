@@ -370,6 +370,7 @@ struct CseHost {
   int pending_set = 0;
   size_t pending_cnt[8] = {};
   int pinned_flip = 0;
+  bool tail_cut = false;                 // hosted emission: the batch was already cut where the frontier collapsed
   bool finished = false;                 // the level loop terminated
 };
 
@@ -446,6 +447,7 @@ int cse_begin(Ctx* c, uint32_t n) {
   H->last_round = 0;
   H->known_nodes = 0;
   H->pending = H->pending_done = H->finished = false;
+  H->tail_cut = false;
   H->pinned_flip = 0;                        // single-batch runs always land in the same pinned buffer
   const int items = int(env_size("BCE_GPU_CSE_ITEMS", 0));
   H->fixed_items = (items == 2 || items == 4) ? items : 0;
@@ -487,6 +489,7 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
   CseDeviceState* h_state = reinterpret_cast<CseDeviceState*>(c->pinned_small.as<char>() + 40 * 1024);
   for (int l = 0; l < 8; ++l) H->args.emit[l] = H->emit_dev[set][l];
   BCE_CUDA(c, cudaEventRecord(c->ev[2], st));
+  bool cut = false;                      // batch ended by the host between two kernels
   for (int hops = 0;; ++hops) {
     if (hops > 100000) { set_error(c, "cse: wide/narrow ping-pong"); return BCE_GPU_E_INTERNAL; }
     const bool was_narrow = H->narrow;
@@ -537,8 +540,19 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
     }
     if (h_state->err) break;
     if (h_state->status == kCseRunning && H->args.max_rounds != 0x7FFFFFFFu) continue;   // stopped on request
-    if (h_state->status == kCseGoWide) { H->narrow = false; continue; }
-    if (h_state->status == kCseGoNarrow) { H->narrow = true; continue; }
+    if (h_state->status == kCseGoWide || h_state->status == kCseGoNarrow) {
+      H->narrow = h_state->status == kCseGoNarrow;
+      // Hosted emission: when the frontier has collapsed, what follows is thousands of short rounds
+      // that emit little.  End the batch here so that its copy to the host runs under that tail
+      // instead of after it.
+      if (H->sets == 2 && !H->tail_cut && H->known_nodes < 2000000ull) {
+        const int par = h_state->round & 1;
+        size_t have = 0;
+        for (int l = 0; l < 8; ++l) have += size_t(h_state->emitted[par][l]);
+        if (have >= (size_t(4) << 20)) { H->tail_cut = true; cut = true; break; }
+      }
+      continue;
+    }
     break;
   }
   BCE_CUDA(c, cudaEventRecord(c->ev[3], st));
@@ -561,7 +575,7 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
     set_error(c, "cse: node frontier exceeded %u nodes per level at round %u", H->args.cap, h_state->round);
     return BCE_GPU_E_FRONTIER;
   }
-  if (h_state->status != kCseDone && h_state->status != kCseDrain) {
+  if (h_state->status != kCseDone && h_state->status != kCseDrain && !cut) {
     set_error(c, "cse: unexpected kernel status %u", h_state->status);
     return BCE_GPU_E_INTERNAL;
   }

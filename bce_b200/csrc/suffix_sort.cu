@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) pack_keys_kernel(const uint8_t* __restric
 // K3: re-rank + stable compaction of the rotations that are still tied
 // ---------------------------------------------------------------------------------
 constexpr int RR_THREADS = 256;
-constexpr int RR_ITEMS = 4;
+constexpr int RR_ITEMS = 8;
 constexpr int RR_TILE = RR_THREADS * RR_ITEMS;
 
 struct RerankArgs {
@@ -107,19 +107,47 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
 
   uint64_t key[RR_ITEMS + 2];     // key[0] = predecessor, key[ITEMS+1] = successor
   uint32_t idx[RR_ITEMS], sap[RR_ITEMS];
+  const bool full = tile * RR_TILE + RR_TILE <= a.m;       // whole tile inside the working set: 16-byte accesses
+  if (full) {
+    const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(a.key + q0);
 #pragma unroll
-  for (int j = 0; j < RR_ITEMS; ++j) {
-    uint32_t q = q0 + j;
-    bool in = q < a.m;
-    key[j + 1] = in ? a.key[q] : 0;
-    idx[j] = in ? a.idx[q] : 0;
-    sap[j] = in ? (a.sapos ? a.sapos[q] : q) : 0;
+    for (int j = 0; j < RR_ITEMS / 2; ++j) {
+      const ulonglong2 v = kp[j];
+      key[2 * j + 1] = v.x;
+      key[2 * j + 2] = v.y;
+    }
+    const uint4* ip = reinterpret_cast<const uint4*>(a.idx + q0);
+#pragma unroll
+    for (int j = 0; j < RR_ITEMS / 4; ++j) {
+      const uint4 v = ip[j];
+      idx[4 * j] = v.x; idx[4 * j + 1] = v.y; idx[4 * j + 2] = v.z; idx[4 * j + 3] = v.w;
+    }
+    if (a.sapos) {
+      const uint4* sp = reinterpret_cast<const uint4*>(a.sapos + q0);
+#pragma unroll
+      for (int j = 0; j < RR_ITEMS / 4; ++j) {
+        const uint4 v = sp[j];
+        sap[4 * j] = v.x; sap[4 * j + 1] = v.y; sap[4 * j + 2] = v.z; sap[4 * j + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < RR_ITEMS; ++j) sap[j] = q0 + j;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < RR_ITEMS; ++j) {
+      uint32_t q = q0 + j;
+      bool in = q < a.m;
+      key[j + 1] = in ? a.key[q] : 0;
+      idx[j] = in ? a.idx[q] : 0;
+      sap[j] = in ? (a.sapos ? a.sapos[q] : q) : 0;
+    }
   }
   key[0] = (q0 > 0 && q0 - 1 < a.m) ? a.key[q0 - 1] : 0;
   key[RR_ITEMS + 1] = (q0 + RR_ITEMS < a.m) ? a.key[q0 + RR_ITEMS] : 0;
 
   // head = first slot of a (new) group; lone = group of one
-  uint32_t head_bits = 0, surv_bits = 0, shead_bits = 0;
+  uint32_t head_bits = 0, surv_bits = 0, shead_bits = 0, lone_bits = 0;
   uint32_t last_head = 0;            // (slot + 1) of the most recent head in this thread
   uint32_t nsurv = 0, nshead = 0;
 #pragma unroll
@@ -130,7 +158,7 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
       bool next_head = (q + 1 == a.m) || key[j + 2] != key[j + 1];
       bool lone = head && next_head;
       if (head) { head_bits |= 1u << j; last_head = q + 1; }
-      if (!lone) { surv_bits |= 1u << j; ++nsurv; }
+      if (!lone) { surv_bits |= 1u << j; ++nsurv; } else lone_bits |= 1u << j;
       if (head && !lone) { shead_bits |= 1u << j; ++nshead; }
     }
   }
@@ -183,6 +211,7 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
   uint32_t gd_run = s_carry[2] + uint32_t(excl64 >> 32);    // surviving heads before this thread
 
   uint32_t cur_head = max(head_before, tile_head_carry);      // (slot+1) of the governing head
+  uint64_t pr[RR_ITEMS];
 #pragma unroll
   for (int j = 0; j < RR_ITEMS; ++j) {
     uint32_t q = q0 + j;
@@ -191,8 +220,10 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
     if (shead_bits >> j & 1u) ++gd_run;
     // slots of one group are consecutive in SA, so the head's SA position is sap - distance
     uint32_t rank = sap[j] - (q - (cur_head - 1));
-    if (!(a.dbg & 2u)) a.sa[sap[j]] = idx[j];
-    if (a.pairs) a.pairs[q] = (uint64_t(idx[j]) << 32) | rank;
+    // SA is final for a slot once its group is a single rotation; tied slots come back next round
+    if ((lone_bits >> j & 1u) && !(a.dbg & 2u)) a.sa[sap[j]] = idx[j];
+    pr[j] = (uint64_t(idx[j]) << 32) | rank;
+    if (a.pairs) { if (!full) a.pairs[q] = pr[j]; }
     else if (!(a.dbg & 1u)) a.rnk[idx[j]] = rank;
     if ((surv_bits >> j & 1u) && !(a.dbg & 4u)) {
       a.idx_out[out_at] = idx[j];
@@ -200,6 +231,11 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
       a.gd_out[out_at] = gd_run - 1;
       ++out_at;
     }
+  }
+  if (a.pairs && full) {
+    ulonglong2* pp = reinterpret_cast<ulonglong2*>(a.pairs + q0);
+#pragma unroll
+    for (int j = 0; j < RR_ITEMS / 2; ++j) pp[j] = make_ulonglong2(pr[2 * j], pr[2 * j + 1]);
   }
   if (tile == a.tiles - 1 && tid == RR_THREADS - 1) {
     a.totals[0] = s_carry[1] + uint32_t(tile_sum);

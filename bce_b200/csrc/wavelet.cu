@@ -17,8 +17,8 @@
 namespace bce {
 
 constexpr int WV_THREADS = 256;
-constexpr int WV_BYTES = 16;                       // per thread
-constexpr int WV_TILE = WV_THREADS * WV_BYTES;     // 4096 positions
+constexpr int WV_BYTES = 64;                       // per thread: two whole rank words
+constexpr int WV_TILE = WV_THREADS * WV_BYTES;     // 16384 positions
 
 __global__ void __launch_bounds__(256) byte_hist_kernel(const uint8_t* __restrict__ L, uint32_t n,
                                                         uint32_t* __restrict__ hist) {
@@ -76,8 +76,30 @@ struct WaveletPass {
   uint32_t* err;
 };
 
+// Copies len bytes from shared memory (any offset) to global memory (any alignment): single bytes up
+// to the first 16-byte boundary of the destination, then 16-byte stores assembled from aligned
+// shared-memory words with funnel shifts, single bytes for the rest.
+__device__ __forceinline__ void copy_run(uint8_t* __restrict__ dst, const uint8_t* s_src, uint32_t len, unsigned tid) {
+  const uint32_t mis = uint32_t(reinterpret_cast<uintptr_t>(dst)) & 15u;
+  const uint32_t head = min(len, (16u - mis) & 15u);
+  if (tid < head) dst[tid] = s_src[tid];
+  const uint32_t chunks = (len - head) / 16;
+  const uint8_t* sb = s_src + head;
+  uint4* d16 = reinterpret_cast<uint4*>(dst + head);
+  const uint32_t sh = (uint32_t(reinterpret_cast<uintptr_t>(sb)) & 3u) * 8;
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb - (sh >> 3));
+  for (uint32_t c = tid; c < chunks; c += WV_THREADS) {
+    const uint32_t* x = sw + c * 4;
+    const uint32_t x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3], x4 = sh ? x[4] : 0u;
+    d16[c] = make_uint4(__funnelshift_r(x0, x1, sh), __funnelshift_r(x1, x2, sh), __funnelshift_r(x2, x3, sh),
+                        __funnelshift_r(x3, x4, sh));
+  }
+  const uint32_t done = head + chunks * 16;
+  if (tid < len - done) dst[done + tid] = s_src[done + tid];
+}
+
 __global__ void __launch_bounds__(WV_THREADS) wavelet_pass_kernel(WaveletPass p) {
-  __shared__ __align__(16) uint8_t s_bytes[WV_TILE];
+  __shared__ __align__(16) uint8_t s_bytes[WV_TILE + 16];
   __shared__ uint32_t s_scan[WV_THREADS / 32];
   __shared__ uint32_t s_tile, s_carry;
 
@@ -89,16 +111,29 @@ __global__ void __launch_bounds__(WV_THREADS) wavelet_pass_kernel(WaveletPass p)
   const uint32_t pos0 = base + tid * WV_BYTES;
   const uint32_t nvalid = pos0 >= p.n ? 0u : min(uint32_t(WV_BYTES), p.n - pos0);
 
-  // input buffers are padded to a multiple of 16 bytes past n, so the vector load is safe
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (nvalid) v = *reinterpret_cast<const uint4*>(p.in + pos0);
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  uint32_t ones16 = 0;
+  // input buffers are padded to a multiple of 64 bytes past n, so the vector loads are safe
+  uint32_t w[16];
+  if (nvalid) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.in + pos0);
 #pragma unroll
-  for (int k = 0; k < 16; ++k) ones16 |= ((w[k >> 2] >> (8 * (k & 3) + p.bit)) & 1u) << k;
-  const uint32_t valid_mask = nvalid >= 16 ? 0xFFFFu : ((1u << nvalid) - 1u);
-  ones16 &= valid_mask;
-  const uint32_t n1 = __popc(ones16), n0 = nvalid - n1;
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = src[q];
+      w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) w[q] = 0;
+  }
+  // bit j of the 64 bytes, position order: 4 bits per 32-bit word
+  uint64_t ones = 0;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const uint32_t t = (w[q] >> p.bit) & 0x01010101u;
+    const uint32_t nib = (t | (t >> 7) | (t >> 14) | (t >> 21)) & 15u;
+    ones |= uint64_t(nib) << (4 * q);
+  }
+  if (nvalid < 64) ones &= (nvalid ? ((1ull << nvalid) - 1ull) : 0ull);
+  const uint32_t n1 = __popcll(ones), n0 = nvalid - n1;
 
   uint32_t tile_zeros;
   const uint32_t z_before_local = block_exclusive_scan<uint32_t, WV_THREADS>(n0, s_scan, tile_zeros);
@@ -110,13 +145,15 @@ __global__ void __launch_bounds__(WV_THREADS) wavelet_pass_kernel(WaveletPass p)
   const uint32_t z_before = s_carry + z_before_local;       // zeros in [0, pos0)
   const uint32_t o_before = pos0 - z_before;                // ones  in [0, pos0)   (pos0 <= n here or unused)
 
-  // (a) rank words: two neighbouring threads make one 32-bit data word
+  // (a) rank words: every thread owns two
   {
-    uint32_t hi = __shfl_down_sync(0xffffffffu, ones16, 1);
-    if (!(tid & 1u)) {
-      uint32_t word = pos0 / 32;
-      if (pos0 <= p.n) p.rank[word] = (uint64_t(ones16 | (hi << 16)) << 32) | o_before;
-    }
+    const uint32_t word = pos0 / 32;
+    const uint32_t lo = uint32_t(ones), hi = uint32_t(ones >> 32);
+    const uint64_t r0 = (uint64_t(lo) << 32) | o_before;
+    const uint64_t r1 = (uint64_t(hi) << 32) | (o_before + __popc(lo));
+    // (a level's words start at an 8-byte boundary only: n/32 + 1 may be odd)
+    if (pos0 <= p.n) p.rank[word] = r0;
+    if (pos0 + 32 <= p.n) p.rank[word + 1] = r1;
   }
   if (!p.out) return;
 
@@ -125,11 +162,22 @@ __global__ void __launch_bounds__(WV_THREADS) wavelet_pass_kernel(WaveletPass p)
     uint32_t zl = z_before_local;
     uint32_t ol = tile_zeros + (tid * WV_BYTES - z_before_local);   // ones before, tile-local
     // positions past n sit at the very end of the last tile and are never copied out
+    if (nvalid == WV_BYTES) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      if (uint32_t(k) < nvalid) {
-        uint8_t b = uint8_t(w[k >> 2] >> (8 * (k & 3)));
-        if ((ones16 >> k) & 1u) s_bytes[ol++] = b; else s_bytes[zl++] = b;
+      for (int k = 0; k < 64; ++k) {
+        const uint8_t b = uint8_t(w[k >> 2] >> (8 * (k & 3)));
+        const uint32_t one = uint32_t(ones >> k) & 1u;
+        s_bytes[one ? ol : zl] = b;
+        ol += one;
+        zl += one ^ 1u;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        if (uint32_t(k) < nvalid) {
+          const uint8_t b = uint8_t(w[k >> 2] >> (8 * (k & 3)));
+          if ((ones >> k) & 1u) s_bytes[ol++] = b; else s_bytes[zl++] = b;
+        }
       }
     }
   }
@@ -138,8 +186,8 @@ __global__ void __launch_bounds__(WV_THREADS) wavelet_pass_kernel(WaveletPass p)
   const uint32_t tile_ones = tile_valid - tile_zeros;
   const uint32_t gz = s_carry;                              // zeros before the tile
   const uint32_t go = p.zeros[p.bit] + (base - s_carry);    // ones region starts at Z_j
-  for (uint32_t u = tid; u < tile_zeros; u += WV_THREADS) p.out[gz + u] = s_bytes[u];
-  for (uint32_t u = tid; u < tile_ones; u += WV_THREADS) p.out[go + u] = s_bytes[tile_zeros + u];
+  copy_run(p.out + gz, s_bytes, tile_zeros, tid);
+  copy_run(p.out + go, s_bytes + tile_zeros, tile_ones, tid);
 }
 
 __global__ void roots_kernel(const uint32_t* __restrict__ zeros, uint32_t* __restrict__ C) {

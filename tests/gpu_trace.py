@@ -11,6 +11,9 @@ from bce_b200 import Frontend, synth  # noqa: E402
 kind, n, seed = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 d = synth.generate(kind, n, seed)
 fe = Frontend(0)
+if os.environ.get("BCE_TRACE_EMIT") == "coder":
+    from bce_b200.gpu import EMIT_CODER
+    fe.set_emit_mode(EMIT_CODER)
 fe.stage_input(d)
 fe.front_resident()
 os.environ["BCE_GPU_TRACE"] = "1"

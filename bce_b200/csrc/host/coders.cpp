@@ -116,7 +116,9 @@ void RangeDecoder::restart_if_narrow(uint64_t total) {              // bce.cpp:5
 uint32_t RangeDecoder::get_uniform(uint32_t range) {                // bce.cpp:592-608
   restart_if_narrow(range);
   const uint64_t step = (hi_ - lo_) / range;
-  const uint32_t sym = uint32_t((code_ - lo_) / step);
+  uint64_t q = (code_ - lo_) / step;
+  if (q >= range) q = range - 1;                // only a damaged stream gets here; the caller's checks end the decode
+  const uint32_t sym = uint32_t(q);
   lo_ += step * sym;
   hi_ = lo_ + step - 1;
   renormalise();

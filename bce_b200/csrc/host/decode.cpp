@@ -2,7 +2,9 @@
 #include "decode.hpp"
 
 #include <array>
+#include <cstdlib>
 #include <memory>
+#include <new>
 
 #include "../../../include/bce_gpu.h"
 #include "coders.hpp"
@@ -15,12 +17,14 @@ namespace bcehost {
 static inline uint64_t shl_x86(uint64_t v, uint64_t count) { return v << (count & 63u); }
 
 uint32_t DecodeRank::ones_before(uint32_t pos) const {
+  if (pos > n_) pos = n_;
   const uint64_t w = w_[pos / 32];
   const uint32_t below = uint32_t(w >> 32) & uint32_t((1ull << (pos % 32)) - 1);
   return uint32_t(w) + uint32_t(__builtin_popcount(below));
 }
 
 void DecodeRank::pin(uint32_t pos, uint32_t ones) {
+  if (pos > n_) return;
   uint64_t need = uint32_t(ones - ones_before(pos));      // ones that still have to move in front of pos
   if (need == 0) return;
   const uint64_t word = pos / 32, o = pos % 32;
@@ -55,8 +59,10 @@ struct Node { uint32_t s, x0, x1; };
 
 // BCE::code with mode = 0, bce.cpp:1236-1373: per round, per level, zero-half then one-half,
 // ascending position; every count comes from the level's own decoder.
-void decode_levels(std::array<std::unique_ptr<StreamDecoder>, 8>& dec, const std::array<uint32_t, 8>& C,
+// Returns false when a count falls outside the interval the dictionary allows (damaged archive).
+bool decode_levels(std::array<std::unique_ptr<StreamDecoder>, 8>& dec, const std::array<uint32_t, 8>& C,
                    std::vector<DecodeRank>& ranks, uint32_t n) {
+  uint64_t visits = 0;
   std::array<std::array<std::vector<Node>, 2>, 8> cur, nxt;
   for (int i = 0; i < 8; ++i)
     if (C[i] && n - C[i]) cur[i][0].push_back({0, C[i], n - C[i]});          // :1238-1240
@@ -69,8 +75,11 @@ void decode_levels(std::array<std::unique_ptr<StreamDecoder>, 8>& dec, const std
       for (int half = 0; half < 2; ++half) {
         for (const Node& nd : cur[i][half]) {
           const uint32_t s = nd.s, x0 = nd.x0, x1 = nd.x1, x = x0 + x1;
+          // a well-formed archive visits 8(n-1) nodes, every one an interval inside [0, n)
+          if (++visits > 8ull * n || !x0 || !x1 || uint64_t(s) + x0 + x1 > n) return false;
           const uint32_t s1 = R.ones_before(s);                               // :1265
           const uint32_t c1 = R.ones_before(s + x) - s1;                      // _1x :1271
+          if (s1 > s || c1 > x) return false;
           const uint32_t s0 = s - s1;
           if (c1 == 0) {                                                      // :1274-1279
             nxt[i][0].push_back({s0, x0, x1});
@@ -86,9 +95,12 @@ void decode_levels(std::array<std::unique_ptr<StreamDecoder>, 8>& dec, const std
           const uint32_t lo = x0 > c1 ? x0 - c1 : 0u;                         // :1290-1294
           const uint32_t hi = x0 - (c1 > x1 ? c1 - x1 : 0u);
           uint32_t z0 = lo;                                                   // _0x0
+          if (hi < lo) return false;
           if (hi != lo) z0 = lo + dec[i]->count(hi - lo + 1, c0, x1, x);     // :1304
+          if (z0 > hi || z0 > c0) return false;
           const uint32_t z1 = c0 - z0;                                        // :1337
           if (z0 && z1) nxt[i][0].push_back({s0, z0, z1});
+          if (z1 > x1 || x1 - z1 > c1) return false;
           const uint32_t o1 = x1 - z1, o0 = c1 - o1;                          // :1343-1344
           if (o0 && o1) nxt[i][1].push_back({one_base + s1, o0, o1});
           R.pin(s + x0, s1 + o0);                                             // :1350
@@ -105,6 +117,7 @@ void decode_levels(std::array<std::unique_ptr<StreamDecoder>, 8>& dec, const std
       }
     }
   }
+  return true;
 }
 
 }  // namespace
@@ -116,12 +129,16 @@ int decode_to_ranks(const std::vector<uint16_t>& a, std::vector<DecodeRank>& ran
   StreamDecoder header(-1, a.data() + 1, header_words);                       // :1179
   n = header.varint();                                                        // :1181
   if (n == 0) return BCE_GPU_E_ARG;
+  if (const char* cap = std::getenv("BCE_HOST_MAX_N"))                        // refuse absurd sizes early (tests, services)
+    if (uint64_t(n) > std::strtoull(cap, nullptr, 10)) return BCE_GPU_E_ARG;
   offset = header.uniform(n + 1);
+  if (offset > n) return BCE_GPU_E_ARG;
   uint32_t size = header.varint();
   std::array<size_t, 9> at{};
   at[0] = 1 + header_words;
   for (int i = 0; i < 7; ++i) {                                               // :1187-1190
     const uint32_t len = header.uniform(size + 1);
+    if (len > size) return BCE_GPU_E_ARG;
     at[i + 1] = at[i] + len;
     size -= len;
   }
@@ -136,9 +153,10 @@ int decode_to_ranks(const std::vector<uint16_t>& a, std::vector<DecodeRank>& ran
   std::array<uint32_t, 8> C;
   for (int i = 0; i < 8; ++i) {                                               // :1208-1211
     C[i] = dec[i]->uniform(n + 1);
+    if (C[i] > n) return BCE_GPU_E_ARG;
     ranks[(i + 7) % 8].pin(n, n - C[i]);
   }
-  decode_levels(dec, C, ranks, n);                                            // :1218
+  if (!decode_levels(dec, C, ranks, n)) return BCE_GPU_E_ARG;                 // :1218
   for (auto& r : ranks) r.finish();                                           // :1220-1223
   return BCE_GPU_OK;
 }
@@ -163,7 +181,12 @@ std::vector<uint8_t> unbwt_serial(const std::vector<DecodeRank>& ranks, uint32_t
 int decode_archive(std::vector<uint16_t>& archive, bool low_memory, std::vector<uint8_t>& out) {
   std::vector<DecodeRank> ranks;
   uint32_t n = 0, offset = 0;
-  int rc = decode_to_ranks(archive, ranks, n, offset);
+  int rc;
+  try {
+    rc = decode_to_ranks(archive, ranks, n, offset);
+  } catch (const std::bad_alloc&) {
+    return BCE_GPU_E_NOMEM;
+  }
   if (rc) return rc;
   std::vector<uint16_t>().swap(archive);                                      // :1203
   if (low_memory) {

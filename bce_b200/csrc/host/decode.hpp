@@ -20,21 +20,28 @@ namespace bcehost {
 // of every word from the next word's base count.
 class DecodeRank {
  public:
-  explicit DecodeRank(uint32_t n) : w_(size_t(n) / 32 + 1, 0) {}
+  explicit DecodeRank(uint32_t n) : w_(size_t(n) / 32 + 1, 0), n_(n) {}
+  // positions are clamped to [0, n]: a corrupt archive must not read outside the dictionary
   uint32_t ones_before(uint32_t pos) const;            // Rank::get<1>, :147-151
   uint32_t zeros_before(uint32_t pos) const { return pos - ones_before(pos); }
-  uint32_t bit(uint32_t pos) const { return uint32_t(w_[pos / 32] >> (pos % 32 + 32)) & 1u; }
+  uint32_t bit(uint32_t pos) const {
+    if (pos > n_) pos = n_;
+    return uint32_t(w_[pos / 32] >> (pos % 32 + 32)) & 1u;
+  }
   void pin(uint32_t pos, uint32_t ones);               // Rank::set, :153-185
   void finish();                                       // Rank::finalize, :187-194
   const std::vector<uint64_t>& words() const { return w_; }
 
  private:
   std::vector<uint64_t> w_;
+  uint32_t n_;
 };
 
 // Decodes a whole archive (uint16 words as read from the file).  low_memory = `-ds`: serial
 // inverse on the host; otherwise the inverse BWT runs on the GPU through bce_gpu_unbwt.
-// Returns 0, or a negative bce_gpu error code.
+// Returns 0, or a negative bce_gpu error code (BCE_GPU_E_ARG for an archive that is not one:
+// every count that comes out of the decoders is checked against the interval it must lie in, so a
+// damaged archive ends in an error, never in an out-of-bounds access or an endless loop).
 int decode_archive(std::vector<uint16_t>& archive, bool low_memory, std::vector<uint8_t>& out);
 
 // Only the host half: header + 8 streams -> the 8 rank dictionaries (after finish()), n, offset.

@@ -122,3 +122,17 @@ def test_host_decoder_rejects_truncated_archives():
     arc = oracle.compress(b"hello world, hello world! the quick brown fox jumps over the lazy dog")
     with pytest.raises(RuntimeError):
         host.decompress(arc[:2], low_memory=True)
+
+
+def test_damaged_archives_never_crash_the_decoder():
+    """the reference's reader trusts the archive; ours must end in an error code
+    (or in some output) for any input, never in an out-of-bounds access or an endless loop."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    env = dict(os.environ, BCE_HOST_MAX_N="100000")
+    script = Path(__file__).resolve().parent / "fuzz_decoder.py"
+    r = subprocess.run([sys.executable, str(script), "7", "1500"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stdout[-300:], r.stderr[-300:])
+    assert "err" in r.stdout.splitlines()[-1]

@@ -12,6 +12,7 @@
 #include <chrono>
 #include <cinttypes>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <string>
@@ -92,22 +93,41 @@ int main(int argc, char** argv) {
       std::printf("Error loading file\n");
       return -1;
     }
+    const bool timing = std::getenv("BCE_TIME") != nullptr;
+    const auto t_read = clock::now();
     bce_gpu_ctx* ctx = nullptr;
     int rc = bce_gpu_open(0, &ctx);
     if (rc) return gpu_failure(ctx, rc);
+    if (timing)
+      std::fprintf(stderr, "[bce] read %.3f s | open device %.3f s\n", std::chrono::duration<double>(t_read - start).count(),
+                   std::chrono::duration<double>(clock::now() - t_read).count());
     uint16_t* words = nullptr;
     size_t nwords = 0;
     rc = bce_compress_buffer(ctx, data.data(), uint32_t(data.size()),
                              reinterpret_cast<const uint8_t*>(table.data()), 8, &words, &nwords);
     if (rc) { gpu_failure(ctx, rc); bce_gpu_close(ctx); return rc; }
-    bce_gpu_close(ctx);
     const std::chrono::duration<double> d = clock::now() - start;
     std::printf("Compressed from %" PRIuMAX " B -> %zu B in %.1f s\n", uintmax_t(data.size()),
                 nwords * sizeof(uint16_t), d.count());
-    std::ofstream archive(argv[2], std::ios::binary | std::ios::trunc);
-    archive.write(reinterpret_cast<const char*>(words), std::streamsize(nwords * sizeof(uint16_t)));
-    bce_host_free(words);
-    return 0;
+    const auto t_write = clock::now();
+    {
+      std::ofstream archive(argv[2], std::ios::binary | std::ios::trunc);
+      archive.write(reinterpret_cast<const char*>(words), std::streamsize(nwords * sizeof(uint16_t)));
+    }
+    const auto t_close = clock::now();
+    if (timing)
+      std::fprintf(stderr, "[bce] write %.3f s\n", std::chrono::duration<double>(t_close - t_write).count());
+    // The archive is on disk.  Unmapping gigabytes of pinned and device memory one allocation at a
+    // time costs up to seconds; leaving that to process exit is what a one-shot tool wants
+    // (BCE_CLEAN_EXIT=1 keeps the orderly teardown for leak checkers).
+    if (std::getenv("BCE_CLEAN_EXIT")) {
+      bce_host_free(words);
+      bce_gpu_close(ctx);
+      return 0;
+    }
+    std::fflush(stdout);
+    std::fflush(stderr);
+    std::_Exit(0);
   }
 
   if (argc == 4 && flag && argv[1][1] == 'd') {                          // bce.cpp:1428-1472

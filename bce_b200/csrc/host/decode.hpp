@@ -28,6 +28,7 @@ class DecodeRank {
     if (pos > n_) pos = n_;
     return uint32_t(w_[pos / 32] >> (pos % 32 + 32)) & 1u;
   }
+  void prefetch(uint32_t pos) const { __builtin_prefetch(&w_[(pos > n_ ? n_ : pos) / 32], 1); }
   void pin(uint32_t pos, uint32_t ones);               // Rank::set, :153-185
   void finish();                                       // Rank::finalize, :187-194
   const std::vector<uint64_t>& words() const { return w_; }

@@ -1,5 +1,7 @@
 // host_api.cpp -- extern "C" surface of libbce_host (include/bce_host.h).
 #include <cstdlib>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <new>
 
@@ -111,22 +113,41 @@ int bce_decode_buffer(const uint16_t* words, size_t nwords, int low_memory, uint
 #ifndef BCE_HOST_NO_GPU
 int bce_compress_buffer(bce_gpu_ctx* ctx, const uint8_t* T, uint32_t n, const uint8_t* cfg288, int threads,
                         uint16_t** words, size_t* nwords) {
+  using clk = std::chrono::steady_clock;
+  auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  const bool timing = std::getenv("BCE_TIME") != nullptr;           // the reference's -DM_TIME lines, per phase
+  const auto t0 = clk::now();
   uint32_t offset = 0, C[8];
   // the device emits coder-ready words: context index and k > 31 halving are done there
   int rc = bce_gpu_set_emit_mode(ctx, BCE_EMIT_CODER, cfg288);
   if (rc) return rc;
   rc = bce_gpu_compress_front(ctx, T, n, &offset, C);               // RankFile ctor, bce.cpp:1411
   if (rc) { bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return rc; }
+  const auto t1 = clk::now();
   bce_archive_writer* w = bce_archive_begin(n, C, cfg288);          // BCE::encode, bce.cpp:1417
   if (!w) { bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return BCE_GPU_E_NOMEM; }
   bce_cse_words batch;
+  double gpu_s = 0, code_s = 0;
+  size_t nbatch = 0, nw = 0;
   do {
+    const auto a = clk::now();
     rc = bce_gpu_cse_next_words(ctx, &batch);
     if (rc) { bce_archive_abort(w); bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return rc; }
+    const auto b = clk::now();
     bce_archive_feed_words(w, &batch, threads);
+    gpu_s += secs(a, b);
+    code_s += secs(b, clk::now());
+    ++nbatch;
+    for (int i = 0; i < 8; ++i) nw += batch.count[i];
   } while (!batch.done);
   bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr);
-  return bce_archive_finish(w, offset, words, nwords);
+  const auto t2 = clk::now();
+  rc = bce_archive_finish(w, offset, words, nwords);
+  if (timing)
+    std::fprintf(stderr, "[bce] front (H2D + BWT + wavelet) %.3f s | level loop waits %.3f s | coders %.3f s (%d threads, "
+                 "%zu words in %zu batches) | finish %.3f s\n", secs(t0, t1), gpu_s, code_s, threads, nw, nbatch,
+                 secs(t2, clk::now()));
+  return rc;
 }
 
 int bce_scan_buffer(bce_gpu_ctx* ctx, const uint8_t* T, uint32_t n, uint8_t cfg288_out[288]) {

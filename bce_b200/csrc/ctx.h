@@ -70,14 +70,24 @@ constexpr size_t kSmallRerankTotals = kSmallRerankTicket + 64;  // 2 u32
 constexpr size_t kSmallWavelet = kSmallRerankTotals + 64;     // 256 u32 hist + 8 u32 zeros + 8 tickets
 constexpr size_t kSmallCse = kSmallWavelet + 2048;            // CseDeviceState
 constexpr size_t kSmallUnbwt = kSmallCse + 1024;              // inverse-BWT counters
+constexpr size_t kSmallPartHist = 48 * 1024;                  // 256 u32      histogram of the rank-scatter partition digit
 constexpr size_t kSmallBytes = 64 * 1024;
 
 // ---- stage entry points (each launches kernels on ctx->stream) --------------------
 // radix_sort.cu: LSD radix sort of (u64 key, u32 value) pairs on digit shifts[0..npass).
 // Buffers are ping-ponged; *out_k / *out_v receive the pointers that hold the result.
+// Where the digit histograms of a sort come from (default: one extra read of the keys).
+struct RadixHistSource {
+  const uint8_t* window_text = nullptr;   // keys are the 8-byte cyclic windows of this text: its byte histogram serves every pass
+  const uint32_t* dev_hist = nullptr;     // [npass][256] already counted on the device (e.g. by the kernel that wrote the keys);
+                                          // may be Ctx::small + kSmallHist itself
+  const uint32_t* host_hist = nullptr;    // [npass][256] known on the host
+};
 int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uint32_t* valB,
                      uint32_t m, const int* shifts, int npass, uint64_t** out_k, uint32_t** out_v,
-                     int* passes_run);
+                     int* passes_run, const RadixHistSource* src = nullptr);
+constexpr int kRadixMaxPasses = 8;
+struct RadixShifts { int s[kRadixMaxPasses]; };
 size_t radix_desc_words(uint32_t m);
 
 // suffix_sort.cu

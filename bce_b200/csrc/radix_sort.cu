@@ -10,34 +10,59 @@
 //
 // HBM traffic per pass: read 12 B + write 12 B per element  (24 m P_r).
 #include <stdlib.h>
+#include <string.h>
 
 #include "ctx.h"
 
 namespace bce {
 
 constexpr int RS_MIN_TILE = 2048;       // smallest tile of any kernel configuration (descriptor sizing)
-constexpr int RS_MAX_PASSES = 8;
+constexpr int RS_MAX_PASSES = kRadixMaxPasses;
 
-struct RadixShifts { int s[RS_MAX_PASSES]; };
 
 size_t radix_desc_words(uint32_t m) { return (size_t(m) / RS_MIN_TILE + 1) * 256; }
 
 // ---- histograms of every digit position in one read ------------------------------
-__global__ void __launch_bounds__(256) radix_hist_kernel(const uint64_t* __restrict__ keys, uint32_t m,
-                                                         int npass, RadixShifts sh,
-                                                         uint32_t* __restrict__ hist) {
-  __shared__ uint32_t h[RS_MAX_PASSES][256];
-  for (int i = threadIdx.x; i < RS_MAX_PASSES * 256; i += blockDim.x) (&h[0][0])[i] = 0;
+// One histogram set per warp (shared-memory atomics of different warps never meet), and a digit
+// on which the whole warp agrees -- the sorted group ids and the high bytes of ranks -- costs one
+// add of 32 instead of 32 serialised adds on one address.
+constexpr int RH_THREADS = 256;
+constexpr int RH_WARPS = RH_THREADS / 32;
+
+__global__ void __launch_bounds__(RH_THREADS) radix_hist_kernel(const uint64_t* __restrict__ keys, uint32_t m,
+                                                                int npass, RadixShifts sh,
+                                                                uint32_t* __restrict__ hist) {
+  extern __shared__ uint32_t rh_smem[];                     // [RH_WARPS][npass][256]
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < RH_WARPS * npass * 256; i += RH_THREADS) rh_smem[i] = 0;
   __syncthreads();
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
-    uint64_t k = keys[i];
-    for (int p = 0; p < npass; ++p) atomicAdd(&h[p][(k >> sh.s[p]) & 255u], 1u);
+  uint32_t* h = rh_smem + size_t(warp) * npass * 256;
+  const uint32_t stride = gridDim.x * RH_THREADS;
+  const uint32_t rounds = (m + stride - 1) / stride;       // the same for every thread: whole warps stay converged
+  uint32_t i = blockIdx.x * RH_THREADS + tid;
+  for (uint32_t r = 0; r < rounds; ++r, i += stride) {
+    const bool in = i < m;
+    const uint64_t k = in ? keys[i] : 0;
+    const unsigned active = __ballot_sync(0xffffffffu, in);
+    if (active == 0xffffffffu) {
+      for (int p = 0; p < npass; ++p) {
+        const uint32_t d = uint32_t(k >> sh.s[p]) & 255u;
+        int same;
+        __match_all_sync(0xffffffffu, d, &same);
+        if (same) { if (lane == 0) h[p * 256 + d] += 32; }
+        else atomicAdd(&h[p * 256 + d], 1u);
+        __syncwarp();
+      }
+    } else if (in) {
+      for (int p = 0; p < npass; ++p) atomicAdd(&h[p * 256 + (uint32_t(k >> sh.s[p]) & 255u)], 1u);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < npass * 256; i += blockDim.x) {
-    uint32_t v = (&h[0][0])[i];
-    if (v) atomicAdd(&hist[i], v);
+  for (int j = tid; j < npass * 256; j += RH_THREADS) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int w = 0; w < RH_WARPS; ++w) v += rh_smem[size_t(w) * npass * 256 + j];
+    if (v) atomicAdd(&hist[j], v);
   }
 }
 
@@ -154,10 +179,11 @@ __global__ void __launch_bounds__(RS_THREADS, MIN_CTAS) radix_onesweep_kernel(Ra
 namespace bce {
 
 static uint32_t g_radix_dbg = 0;
+void byte_hist_launch(Ctx* c, const uint8_t* L, uint32_t n, uint32_t* d_hist);   // wavelet.cu
 
 int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uint32_t* valB,
                      uint32_t m, const int* shifts, int npass, uint64_t** out_k, uint32_t** out_v,
-                     int* passes_run) {
+                     int* passes_run, const RadixHistSource* src) {
   *out_k = keyA;
   *out_v = valA;
   if (passes_run) *passes_run = 0;
@@ -175,14 +201,42 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
 
   RadixShifts sh;
   for (int i = 0; i < RS_MAX_PASSES; ++i) sh.s[i] = i < npass ? shifts[i] : 0;
-  BCE_CUDA(c, cudaMemsetAsync(d_hist, 0, kSmallErr, c->stream));   // hist, base, tickets (err is the caller's)
-  uint64_t hb64 = (uint64_t(m) + 255) / 256, hbmax = uint64_t(c->sm_count) * 8;
-  int hb = int(hb64 < hbmax ? hb64 : hbmax);
-  radix_hist_kernel<<<hb, 256, 0, c->stream>>>(keyA, m, npass, sh, d_hist);
-  c->stats.gpu_launches++;
-  BCE_CUDA(c, cudaGetLastError());
-  BCE_CUDA(c, cudaMemcpyAsync(h_hist, d_hist, npass * 256 * 4, cudaMemcpyDeviceToHost, c->stream));
-  BCE_CUDA(c, cudaStreamSynchronize(c->stream));
+  const uint8_t* window_text = src ? src->window_text : nullptr;
+  const uint32_t* dev_hist = src ? src->dev_hist : nullptr;
+  const uint32_t* host_hist = src ? src->host_hist : nullptr;
+  // hist, base, tickets (err is the caller's); a histogram that already sits in d_hist stays
+  if (dev_hist == d_hist) BCE_CUDA(c, cudaMemsetAsync(d_base, 0, kSmallErr - kSmallBase, c->stream));
+  else BCE_CUDA(c, cudaMemsetAsync(d_hist, 0, kSmallErr, c->stream));
+  if (host_hist) {
+    memcpy(h_hist, host_hist, size_t(npass) * 256 * 4);
+  } else if (dev_hist) {
+    BCE_CUDA(c, cudaMemcpyAsync(h_hist, dev_hist, npass * 256 * 4, cudaMemcpyDeviceToHost, c->stream));
+    BCE_CUDA(c, cudaStreamSynchronize(c->stream));
+  } else if (window_text) {
+    // keys are the 8-byte cyclic windows of a text: byte p of key i is T[(i + 7 - p) mod n], so every
+    // digit position has the byte histogram of the text -- one read of n bytes instead of 8n
+    byte_hist_launch(c, window_text, m, d_hist);
+    c->stats.gpu_launches++;
+    BCE_CUDA(c, cudaGetLastError());
+    BCE_CUDA(c, cudaMemcpyAsync(h_hist, d_hist, 256 * 4, cudaMemcpyDeviceToHost, c->stream));
+    BCE_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int p = npass - 1; p >= 0; --p)
+      for (int d = 0; d < 256; ++d) h_hist[p * 256 + d] = h_hist[d];
+  } else {
+    static bool hist_attr = false;
+    const size_t hsmem = size_t(RH_WARPS) * npass * 256 * 4;
+    if (!hist_attr) {
+      BCE_CUDA(c, cudaFuncSetAttribute(radix_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RH_WARPS * RS_MAX_PASSES * 1024));
+      hist_attr = true;
+    }
+    uint64_t hb64 = (uint64_t(m) + 255) / 256, hbmax = uint64_t(c->sm_count) * 3;
+    int hb = int(hb64 < hbmax ? hb64 : hbmax);
+    radix_hist_kernel<<<hb, RH_THREADS, hsmem, c->stream>>>(keyA, m, npass, sh, d_hist);
+    c->stats.gpu_launches++;
+    BCE_CUDA(c, cudaGetLastError());
+    BCE_CUDA(c, cudaMemcpyAsync(h_hist, d_hist, npass * 256 * 4, cudaMemcpyDeviceToHost, c->stream));
+    BCE_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
 
   // exclusive scans on the host (8 x 256 values); passes whose digit is constant are skipped
   bool run[RS_MAX_PASSES];
@@ -314,7 +368,7 @@ extern "C" int bce_gpu_dbg_radix(bce_gpu_ctx* h, uint32_t m, int npass, int flag
   g_radix_dbg = uint32_t(flags);
   BCE_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
   uint64_t* ok; uint32_t* ov; int ran = 0;
-  int rc = radix_sort_pairs(c, kA, kB, vA, vB, m, shifts, npass, &ok, &ov, &ran);
+  int rc = radix_sort_pairs(c, kA, kB, vA, vB, m, shifts, npass, &ok, &ov, &ran, nullptr);
   g_radix_dbg = 0;
   BCE_TRY(rc);
   BCE_CUDA(c, cudaEventRecord(c->ev[1], c->stream));

@@ -253,25 +253,88 @@ __global__ void __launch_bounds__(256) scatter_ranks_kernel(const uint64_t* __re
 }
 
 // ---------------------------------------------------------------------------------
-// K4: key rebuild for the next doubling step (gather-bound)
+// K4: key rebuild for the next doubling step (gather-bound) + the histograms of what it wrote
 // ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rekey_kernel(const uint32_t* __restrict__ idx,
-                                                    const uint32_t* __restrict__ gd,
-                                                    const uint32_t* __restrict__ rnk, uint32_t m,
-                                                    uint32_t n, uint32_t h, int tiebreak,
-                                                    uint64_t* __restrict__ key) {
-  uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= m) return;
-  uint32_t i = idx[q];
-  uint32_t second;
-  if (tiebreak) {
-    second = i;                       // identical rotations: order by start index
-  } else {
-    uint64_t j = uint64_t(i) + h;
-    if (j >= n) j -= n;
-    second = rnk[j];
+// The kernel waits on random 4-byte gathers, so counting the digits of the keys it has in registers
+// is free: the sort that follows needs no histogram pass over the keys, and neither does the pass
+// that partitions the rank scatter by the top bits of idx.
+struct RekeyHist {
+  RadixShifts sh;
+  int npass;
+  uint32_t* hist;       // [npass][256]
+  uint32_t* phist;      // [256]: digit (idx >> pshift), or NULL
+  int pshift;
+};
+constexpr int RK_THREADS = 256;
+constexpr int RK_ITEMS = 4;
+
+__device__ __forceinline__ void hist_add(uint32_t* set, uint32_t d, bool full_warp, unsigned lane) {
+  if (full_warp) {                       // one add of 32 where the whole warp agrees (sorted group ids, high rank bytes)
+    const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+    if (__all_sync(0xffffffffu, d == d0)) {
+      if (lane == 0) atomicAdd(&set[d0], 32u);
+      return;
+    }
   }
-  key[q] = (uint64_t(gd[q]) << 32) | second;
+  atomicAdd(&set[d], 1u);
+}
+
+__global__ void __launch_bounds__(RK_THREADS) rekey_kernel(const uint32_t* __restrict__ idx,
+                                                           const uint32_t* __restrict__ gd,
+                                                           const uint32_t* __restrict__ rnk, uint32_t m,
+                                                           uint32_t n, uint32_t h, int tiebreak,
+                                                           uint64_t* __restrict__ key, RekeyHist rh) {
+  __shared__ uint32_t s_hist[2][kRadixMaxPasses + 1][256];        // two sets: even and odd warps
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 2 * (kRadixMaxPasses + 1) * 256; i += RK_THREADS) (&s_hist[0][0][0])[i] = 0;
+  __syncthreads();
+  uint32_t (*set)[256] = s_hist[warp & 1];
+  const uint32_t chunk = RK_THREADS * RK_ITEMS;
+  for (uint64_t base = uint64_t(blockIdx.x) * chunk; base < m; base += uint64_t(gridDim.x) * chunk) {
+    uint32_t i[RK_ITEMS], second[RK_ITEMS], g[RK_ITEMS];
+    bool in[RK_ITEMS];
+#pragma unroll
+    for (int u = 0; u < RK_ITEMS; ++u) {
+      const uint64_t q = base + uint64_t(u) * RK_THREADS + tid;
+      in[u] = q < m;
+      i[u] = in[u] ? idx[q] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < RK_ITEMS; ++u) {
+      if (tiebreak) {
+        second[u] = i[u];                 // identical rotations: order by start index
+      } else {
+        uint64_t j = uint64_t(i[u]) + h;
+        if (j >= n) j -= n;
+        second[u] = in[u] ? rnk[j] : 0u;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RK_ITEMS; ++u) {
+      const uint64_t q = base + uint64_t(u) * RK_THREADS + tid;
+      g[u] = in[u] ? gd[q] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < RK_ITEMS; ++u) {
+      const uint64_t q = base + uint64_t(u) * RK_THREADS + tid;
+      const uint64_t k = (uint64_t(g[u]) << 32) | second[u];
+      if (in[u]) key[q] = k;
+      const bool full_warp = __ballot_sync(0xffffffffu, in[u]) == 0xffffffffu;
+      if (in[u] || full_warp) {
+        for (int p = 0; p < rh.npass; ++p) hist_add(set[p], uint32_t(k >> rh.sh.s[p]) & 255u, full_warp, lane);
+        if (rh.phist) hist_add(set[kRadixMaxPasses], (i[u] >> rh.pshift) & 255u, full_warp, lane);
+      }
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < rh.npass * 256; j += RK_THREADS) {
+    const uint32_t v = s_hist[0][j >> 8][j & 255] + s_hist[1][j >> 8][j & 255];
+    if (v) atomicAdd(&rh.hist[j], v);
+  }
+  if (rh.phist) {
+    const uint32_t v = s_hist[0][kRadixMaxPasses][tid] + s_hist[1][kRadixMaxPasses][tid];
+    if (v) atomicAdd(&rh.phist[tid], v);
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -329,6 +392,8 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
   uint32_t* d_err = reinterpret_cast<uint32_t*>(small + kSmallErr);
   uint32_t* d_ticket = reinterpret_cast<uint32_t*>(small + kSmallRerankTicket);
   uint32_t* d_totals = reinterpret_cast<uint32_t*>(small + kSmallRerankTotals);
+  uint32_t* d_hist = reinterpret_cast<uint32_t*>(small + kSmallHist);
+  uint32_t* d_phist = reinterpret_cast<uint32_t*>(small + kSmallPartHist);
   uint32_t* h_small = c->pinned_small.as<uint32_t>() + 8192;   // past the sort's host mirror
   BCE_CUDA(c, cudaMemsetAsync(d_err, 0, 64, st));
 
@@ -370,6 +435,10 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     if (round >= kMaxSortRounds) { set_error(c, "suffix sort: too many rounds"); return BCE_GPU_E_INTERNAL; }
     int shifts[8], np = 0;
     bool tiebreak = false;
+    // Large working sets update the rank array through pairs partitioned by the top 8 bits of idx
+    // (see the re-rank step below); decided here because the key rebuild counts that digit too.
+    const bool partitioned = !getenv("BCE_GPU_NO_PARTITION") && m >= (8u << 20) && size_t(n) * 4 > (size_t(64) << 20);
+    const int pshift = 32 + std::max(0, nbits - 8);
     if (round == 0) {
       for (int s = 0; s < 64; s += 8) shifts[np++] = s;
     } else {
@@ -377,16 +446,28 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
       for (int s = 0; s < nbits; s += 8) shifts[np++] = s;
       int gbits = bits_for(groups);
       for (int s = 0; s < gbits && np < 8; s += 8) shifts[np++] = 32 + s;
-      // working-set slot -> key of the next doubling step
-      rekey_kernel<<<(m + 255) / 256, 256, 0, st>>>(vcur, gd_next == gdA ? gdB : gdA, rnk, m, n,
-                                                    uint32_t(tiebreak ? 0 : h), tiebreak ? 1 : 0, kcur);
+      // working-set slot -> key of the next doubling step, digit histograms counted on the way
+      RekeyHist rh;
+      for (int i = 0; i < kRadixMaxPasses; ++i) rh.sh.s[i] = i < np ? shifts[i] : 0;
+      rh.npass = np;
+      rh.hist = d_hist;
+      rh.phist = partitioned ? d_phist : nullptr;
+      rh.pshift = pshift - 32;
+      BCE_CUDA(c, cudaMemsetAsync(d_hist, 0, kRadixMaxPasses * 256 * 4, st));
+      BCE_CUDA(c, cudaMemsetAsync(d_phist, 0, 256 * 4, st));
+      const uint32_t chunk = RK_THREADS * RK_ITEMS;
+      const uint32_t want = (m + chunk - 1) / chunk, most = uint32_t(c->sm_count) * 8;
+      rekey_kernel<<<want < most ? want : most, RK_THREADS, 0, st>>>(vcur, gd_next == gdA ? gdB : gdA, rnk, m, n,
+                                                                     uint32_t(tiebreak ? 0 : h), tiebreak ? 1 : 0, kcur, rh);
       S.gpu_launches++;
       BCE_CUDA(c, cudaGetLastError());
       BCE_TRY(lap(S.ms_rekey));
     }
     BCE_TRACE("sort round %d m=%u h=%llu tiebreak=%d passes<=%d", round, m, (unsigned long long)h, int(tiebreak), np);
     uint64_t* ks; uint32_t* vs; int ran = 0;
-    BCE_TRY(radix_sort_pairs(c, kcur, kalt, vcur, valt, m, shifts, np, &ks, &vs, &ran));
+    RadixHistSource hsrc;
+    if (round == 0) hsrc.window_text = T; else hsrc.dev_hist = d_hist;
+    BCE_TRY(radix_sort_pairs(c, kcur, kalt, vcur, valt, m, shifts, np, &ks, &vs, &ran, &hsrc));
     BCE_TRY(lap(S.ms_radix));
     S.sort_m[round] = m;
     S.sort_passes[round] = uint32_t(ran);
@@ -402,7 +483,6 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     // sector).  Write (idx, rank) pairs in slot order instead, partition them by the top 8 bits
     // of idx with one keys-only radix pass, and scatter from that order: every 1/256 slice of
     // the rank array then stays in L2 while it is being filled.
-    const bool partitioned = !getenv("BCE_GPU_NO_PARTITION") && m >= (8u << 20) && size_t(n) * 4 > (size_t(64) << 20);
     uint64_t* pair_buf = (ks == keyA) ? keyB : keyA;
     a.pairs = partitioned ? pair_buf : nullptr;
     a.idx_out = v_other; a.sapos_out = sap_next; a.gd_out = gd_next;
@@ -425,9 +505,20 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
       BCE_TRACE("rerank round %d m=%u: %.3f ms (dbg=%u, partitioned=%d)", round, m, S.ms_rerank - before, a.dbg, int(partitioned));
       if (a.dbg) { set_error(c, "rerank timing experiment"); return BCE_GPU_E_INTERNAL; } }
     if (partitioned) {
-      const int pshift = 32 + std::max(0, nbits - 8);
       uint64_t* pk; uint32_t* pv; int pran = 0;
-      BCE_TRY(radix_sort_pairs(c, pair_buf, ks, nullptr, nullptr, m, &pshift, 1, &pk, &pv, &pran));
+      RadixHistSource psrc;
+      uint32_t all_idx[256];
+      if (round == 0) {                  // every idx in [0, n) is present: the digit counts are arithmetic
+        const int sft = pshift - 32;
+        for (uint32_t d = 0; d < 256; ++d) {
+          const uint64_t lo = uint64_t(d) << sft, hi = uint64_t(d + 1) << sft;
+          all_idx[d] = uint32_t(lo >= n ? 0 : (hi < n ? hi : n) - lo);
+        }
+        psrc.host_hist = all_idx;
+      } else {
+        psrc.dev_hist = d_phist;          // counted by rekey_kernel over this round's working set
+      }
+      BCE_TRY(radix_sort_pairs(c, pair_buf, ks, nullptr, nullptr, m, &pshift, 1, &pk, &pv, &pran, &psrc));
       scatter_ranks_kernel<<<(m + 255) / 256, 256, 0, st>>>(pk, m, rnk);
       S.gpu_launches++;
       BCE_CUDA(c, cudaGetLastError());

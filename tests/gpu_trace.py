@@ -15,7 +15,8 @@ if os.environ.get("BCE_TRACE_EMIT") == "coder":
     from bce_b200.gpu import EMIT_CODER
     fe.set_emit_mode(EMIT_CODER)
 fe.stage_input(d)
-fe.front_resident()
+if os.environ.get("BCE_TRACE_WARM", "1") != "0":
+    fe.front_resident()
 os.environ["BCE_GPU_TRACE"] = "1"
 fe.front_resident()
 os.environ["BCE_GPU_TRACE"] = "0"

@@ -264,14 +264,20 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
     {radix_onesweep_kernel<384, 12, 2>, 384, 12},
     {radix_onesweep_kernel<256, 8, 4>, 256, 8},
     {radix_onesweep_kernel<512, 12, 1>, 512, 12},
+    {radix_onesweep_kernel<256, 20, 3>, 256, 20},
+    {radix_onesweep_kernel<256, 24, 2>, 256, 24},
+    {radix_onesweep_kernel<256, 28, 2>, 256, 28},
+    {radix_onesweep_kernel<256, 32, 2>, 256, 32},
+    {radix_onesweep_kernel<384, 16, 2>, 384, 16},
+    {radix_onesweep_kernel<512, 16, 1>, 512, 16},
   };
-  int which_cfg = 1;          // 256 x 16: fastest on B200 (400 MB text: 62.2 ms of radix kernels; 256 x 12: 66.2, 512 x 8: 75.2)
-  { const char* v = getenv("BCE_GPU_RADIX_CFG"); if (v && *v >= '0' && *v <= '5') which_cfg = *v - '0'; }
+  int which_cfg = 7;          // 256 x 24, 2 CTAs/SM: fastest on B200 on real keys (1 GB text, radix stage: 125 ms; 256 x 16 x 3 CTAs: 140; 256 x 20 x 3: 134; 256 x 28 x 2: 129; 384 x 16 x 2: 149; 512 x 16 x 1: 166)
+  { const char* v = getenv("BCE_GPU_RADIX_CFG"); if (v && *v >= '0' && *v <= '9') which_cfg = *v - '0'; else if (v && *v >= 'a' && *v <= 'b') which_cfg = 10 + *v - 'a'; }
   const Cfg& cfg = cfgs[which_cfg];
   const int RS_TILE = cfg.threads * cfg.items;
   const int RS_THREADS = cfg.threads;
   const size_t rs_smem = size_t(RS_TILE) * 12 + size_t(cfg.threads / 32) * 1024;
-  static bool attr_set[6] = {};
+  static bool attr_set[12] = {};
   if (!attr_set[which_cfg]) {
     BCE_CUDA(c, cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem)));
     attr_set[which_cfg] = true;

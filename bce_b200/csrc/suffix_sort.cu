@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) pack_keys_kernel(const uint8_t* __restric
 // K3: re-rank + stable compaction of the rotations that are still tied
 // ---------------------------------------------------------------------------------
 constexpr int RR_THREADS = 256;
-constexpr int RR_ITEMS = 8;
+constexpr int RR_ITEMS = 16;
 constexpr int RR_TILE = RR_THREADS * RR_ITEMS;
 
 struct RerankArgs {

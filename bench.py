@@ -269,8 +269,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         k_ms = cse_ms / k_launches
         note = "one launch runs all rounds of the level loop"
     achieved = k_bytes / (k_ms / 1e3) / 1e9
+    traffic, traffic_src = None, None
+    try:                                   # measured DRAM bytes per algorithmic byte (ncu), see profiles/r1_traffic.json
+        tj = json.loads((Path(__file__).resolve().parent / "profiles" / "r1_traffic.json").read_text())
+        ent = tj["radix_onesweep_kernel" if radix_ms >= cse_ms else "cse_level_loop"]
+        traffic, traffic_src = ent["ratio"] * k_bytes, f"{ent['ratio']} x algorithmic bytes of this launch; " + ent["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": k_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "launches_per_step": k_launches,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "launches_per_step": k_launches,
                 "ms_per_launch": k_ms, "note": note,
                 "whole_path": {"algorithmic_bytes": ab["total"], "GBps": ab["total"] / (st["ms_total"] / 1e3) / 1e9,
                                "frac": ab["total"] / (st["ms_total"] / 1e3) / 1e9 / peak,

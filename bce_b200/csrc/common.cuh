@@ -105,6 +105,10 @@ __device__ __forceinline__ uint64_t desc_load(const uint64_t* p) {
 // Spin until the descriptor carries `tag`.  The budget bounds the wait so that a logic
 // error surfaces as BCE_GPU_E_INTERNAL instead of a hung GPU.
 constexpr uint32_t kSpinBudget = 1u << 18;
+#ifndef BCE_SPIN_HOT
+#define BCE_SPIN_HOT 64
+#define BCE_SPIN_SLEEP 20
+#endif
 __device__ __forceinline__ uint64_t desc_wait(const uint64_t* p, uint32_t tag, uint32_t* err) {
   uint64_t w = desc_load(p);
   uint32_t spins = 0;
@@ -113,7 +117,7 @@ __device__ __forceinline__ uint64_t desc_wait(const uint64_t* p, uint32_t tag, u
       atomicExch(err, 1u);
       return desc_pack(tag, kDescPrefix, 0);
     }
-    if (spins > 64) __nanosleep(20);      // poll hot at first: the usual wait is one L2 round trip
+    if (spins > BCE_SPIN_HOT) __nanosleep(BCE_SPIN_SLEEP);      // poll hot at first: the usual wait is one L2 round trip
     w = desc_load(p);
   }
   return w;

@@ -43,10 +43,9 @@ enum : uint32_t { kCseRunning = 0, kCseDone = 1, kCseDrain = 2, kCseOverflow = 3
                   kCseGoWide = 5, kCseGoNarrow = 6 };
 enum : uint32_t { kEmitRaw = 0, kEmitCoder = 1, kEmitScan = 2 };
 
-constexpr int NR_THREADS = 1024;
-constexpr int NR_CAP = 1024;                       // nodes per level held in shared memory
-constexpr uint32_t kNarrowLeave = NR_CAP / 2;      // a node has <= 2 children: the next round always fits
-constexpr uint32_t kNarrowEnter = NR_CAP / 4;      // wide -> narrow once every level is at most this
+constexpr uint32_t kNarrowEnter = 256;     // every level at most this: the one-node-per-thread cluster kernel (leaves above 512)
+constexpr int NM_THREADS = 512, NM_K = 8;  // the 8-nodes-per-thread instance: 4096 nodes per level
+constexpr uint32_t kMediumEnter = NM_THREADS * NM_K / 4;   // entered at <= 1024 per level, left above 2048
 
 struct CseDeviceState {
   uint32_t cnt[2][8][2];                 // [round parity][level][half] frontier sizes
@@ -74,7 +73,9 @@ struct CseArgs {
   uint32_t desc_tiles;
   uint32_t max_rounds;
   uint32_t round_limit;                  // no input needs more than 8 n rounds: beyond it something is broken
-  uint32_t use_narrow;                   // 1 = hand narrow frontiers to the cluster kernel
+  uint32_t use_narrow;                   // 1 = hand narrow frontiers to the cluster kernels
+  uint32_t narrow_enter;                 // ... once every level holds at most this many nodes
+  uint32_t use_tiny, tiny_enter;         // 1 = the one-CTA kernel takes frontiers of <= tiny_enter nodes per level
   uint32_t dbg;                          // timing experiments only (results become wrong): 1 no look-back, 2 no gathers, 4 no flush
   uint32_t emit_mode;                    // kEmitRaw / kEmitCoder / kEmitScan
   unsigned long long min_nodes, max_nodes;   // wide kernel: leave (kCseGoWide) when the frontier is outside
@@ -154,6 +155,12 @@ __device__ __forceinline__ bool grid_barrier(CseDeviceState* S, unsigned long lo
   return ok;
 }
 
+// The barrier's targets are multiples of gridDim.x: a launch with another grid size starts a new count.
+__global__ void cse_reset_barrier_kernel(CseDeviceState* S) {
+  S->arrivals = 0;
+  S->barriers = 0;
+}
+
 __global__ void cse_init_kernel(CseArgs a, uint32_t n) {
   // roots: node (0, C[i], n - C[i]) in the zero-half of level i when both are non-zero
   // (bce.cpp:1238-1240)
@@ -201,18 +208,27 @@ namespace bce {
 // ---------------------------------------------------------------------------------
 // narrow mode: one cluster, one CTA per level
 // ---------------------------------------------------------------------------------
+// THREADS x K nodes per level fit: <1024, 1> for the long tail of tiny frontiers, <512, 8> (8 nodes
+// per thread, 24 rank words in flight) for frontiers of a few thousand nodes per level, where a
+// round of the wide kernel is five dependent trips to global memory plus a grid barrier.
+template <int THREADS, int K>
 struct NarrowShared {
-  uint32_t s[2][NR_CAP], a[2][NR_CAP], b[2][NR_CAP];   // this level's frontier, double buffered
+  static constexpr int CAP = THREADS * K;
+  uint32_t s[2][CAP], a[2][CAP], b[2][CAP];             // this level's frontier, double buffered
   uint32_t cz[2], co[2];                                // zero-/one-half sizes of buffer p
   uint32_t all_cnt[2][8];                               // every level's frontier size (all-gathered)
   unsigned long long all_emitted[2][8];                 // every level's emission cursor (all-gathered)
-  uint64_t scan[NR_THREADS / 32];
+  uint64_t scan[THREADS / 32];
   uint32_t decision;
 };
 
-__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_narrow_kernel(CseArgs a) {
+template <int THREADS, int K>
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(THREADS, 1) cse_narrow_kernel(CseArgs a) {
+  using Shared = NarrowShared<THREADS, K>;
+  constexpr uint32_t CAP = Shared::CAP;
   cg::cluster_group cluster = cg::this_cluster();
-  __shared__ NarrowShared sh;
+  extern __shared__ __align__(16) unsigned char narrow_smem[];
+  Shared& sh = *reinterpret_cast<Shared*>(narrow_smem);
   const unsigned tid = threadIdx.x;
   const int l = int(cluster.block_rank());          // level handled by this CTA
   const int ln = (l + 1) & 7;
@@ -226,7 +242,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_n
   {
     const uint32_t cz = S->cnt[gpar][l][0], co = S->cnt[gpar][l][1];
     if (tid == 0) { sh.cz[0] = cz; sh.co[0] = co; }
-    for (uint32_t t = tid; t < cz + co && t < NR_CAP; t += NR_THREADS) {
+    for (uint32_t t = tid; t < cz + co && t < CAP; t += THREADS) {
       const uint32_t idx = t < cz ? t : a.cap - 1 - (t - cz);
       sh.s[0][t] = a.fs[gpar][l][idx];
       sh.a[0][t] = a.fa[gpar][l][idx];
@@ -254,7 +270,9 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_n
       }
       sh.decision = total == 0 ? kCseDone
                   : round >= a.round_limit ? kCseRunaway
-                  : widest > kNarrowLeave ? kCseGoWide
+                  : widest > CAP / 2 ? kCseGoWide                   // a node has <= 2 children: the next round always fits
+                  : (K > 1 && widest <= kNarrowEnter) ? kCseGoNarrow   // the one-node-per-thread instance is quicker there
+                  : (K == 1 && a.use_tiny && widest <= a.tiny_enter) ? kCseGoNarrow   // and the one-CTA kernel for a handful of nodes
                   : drain ? kCseDrain : kCseRunning;
       if (sh.decision == kCseRunning) { visits += total; peak = max(peak, (unsigned long long)total); }
     }
@@ -262,49 +280,75 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_n
     status = sh.decision;
     if (status != kCseRunning) break;
 
-    const uint32_t cz = sh.cz[p], co = sh.co[p];
-    const bool live = tid < cz + co;
-    uint32_t s = 0, x0 = 0, x1 = 0;
-    if (live) { s = sh.s[p][tid]; x0 = sh.a[p][tid]; x1 = sh.b[p][tid]; }
-    uint32_t fz = 0, fo = 0, nw = 0, s0 = 0, s1 = 0, c1 = 0, z0 = 0, e0 = 0, e1 = 0, e2 = 0;
-    uint32_t za0 = 0, za1 = 0, oa0 = 0, oa1 = 0;
-    const uint32_t x = x0 + x1;
-    if (live) {
-      const uint64_t wa = __ldg(R + (s >> 5));
-      const uint64_t wb = __ldg(R + ((s + x) >> 5));
-      const uint64_t wc = __ldg(R + ((s + x0) >> 5));
-      s1 = rank1_word(wa, s);
-      c1 = rank1_word(wb, s + x) - s1;
-      s0 = s - s1;
-      z0 = (s + x0 - rank1_word(wc, s + x0)) - s0;
-      if (c1 == 0) { fz = 1; za0 = x0; za1 = x1; }
-      else if (c1 == x) { fo = 1; oa0 = x0; oa1 = x1; }
-      else {
-        const uint32_t c0 = x - c1;
-        const uint32_t lo = x0 > c1 ? x0 - c1 : 0u;
-        const uint32_t hi = x0 - (c1 > x1 ? c1 - x1 : 0u);
-        const uint32_t z1 = c0 - z0, o1 = x1 - z1, o0c = c1 - o1;
-        if (hi != lo) nw = count_words(a, l, z0 - lo, hi - lo + 1, c0, x1, x, e0, e1, e2);   // bce.cpp:1302
-        if (z0 && z1) { fz = 1; za0 = z0; za1 = z1; }
-        if (o0c && o1) { fo = 1; oa0 = o0c; oa1 = o1; }
+    const uint32_t cnt = sh.cz[p] + sh.co[p];
+    uint32_t s[K], x0[K], x1[K];
+    uint64_t wa[K], wb[K], wc[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const uint32_t t = tid * K + j;
+      const bool live = t < cnt;
+      s[j] = live ? sh.s[p][t] : 0u;
+      x0[j] = live ? sh.a[p][t] : 0u;
+      x1[j] = live ? sh.b[p][t] : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (tid * K + j < cnt) {
+        wa[j] = __ldg(R + (s[j] >> 5));
+        wb[j] = __ldg(R + ((s[j] + x0[j] + x1[j]) >> 5));
+        wc[j] = __ldg(R + ((s[j] + x0[j]) >> 5));
+      } else { wa[j] = wb[j] = wc[j] = 0; }
+    }
+    uint32_t fz = 0, fo = 0, nwsum = 0;
+    uint32_t cs0[K], ca[K], cb[K], cs1[K], oa[K], ob[K];       // zero-child and one-child of every node
+    uint32_t e0[K], e1[K], e2[K], nw[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      cs0[j] = ca[j] = cb[j] = cs1[j] = oa[j] = ob[j] = e0[j] = e1[j] = e2[j] = nw[j] = 0;
+      if (tid * K + j < cnt) {
+        const uint32_t x = x0[j] + x1[j];
+        const uint32_t s1 = rank1_word(wa[j], s[j]);
+        const uint32_t c1 = rank1_word(wb[j], s[j] + x) - s1;
+        const uint32_t s0 = s[j] - s1;
+        const uint32_t z0 = (s[j] + x0[j] - rank1_word(wc[j], s[j] + x0[j])) - s0;
+        cs0[j] = s0;
+        cs1[j] = a.C[ln] + s1;
+        if (c1 == 0) { fz |= 1u << j; ca[j] = x0[j]; cb[j] = x1[j]; }
+        else if (c1 == x) { fo |= 1u << j; oa[j] = x0[j]; ob[j] = x1[j]; }
+        else {
+          const uint32_t c0 = x - c1;
+          const uint32_t lo = x0[j] > c1 ? x0[j] - c1 : 0u;
+          const uint32_t hi = x0[j] - (c1 > x1[j] ? c1 - x1[j] : 0u);
+          const uint32_t z1 = c0 - z0, o1 = x1[j] - z1, o0c = c1 - o1;
+          if (hi != lo) nw[j] = count_words(a, l, z0 - lo, hi - lo + 1, c0, x1[j], x, e0[j], e1[j], e2[j]);   // bce.cpp:1302
+          if (z0 && z1) { fz |= 1u << j; ca[j] = z0; cb[j] = z1; }
+          if (o0c && o1) { fo |= 1u << j; oa[j] = o0c; ob[j] = o1; }
+        }
+        nwsum += nw[j];
       }
     }
-    const uint64_t mine = uint64_t(fz) | (uint64_t(fo) << 21) | (uint64_t(nw) << 42);
+    const uint64_t mine = uint64_t(__popc(fz)) | (uint64_t(__popc(fo)) << 21) | (uint64_t(nwsum) << 42);
     uint64_t tot;
-    const uint64_t excl = block_exclusive_scan<uint64_t, NR_THREADS>(mine, sh.scan, tot);
+    const uint64_t excl = block_exclusive_scan<uint64_t, THREADS>(mine, sh.scan, tot);
     const uint32_t tz = uint32_t(tot) & 0x1FFFFFu, to = uint32_t(tot >> 21) & 0x1FFFFFu, te = uint32_t(tot >> 42) & 0x1FFFFFu;
     const int q = p ^ 1;
     // the next level's CTA receives its frontier directly in its shared memory
     uint32_t* rs = cluster.map_shared_rank(&sh.s[q][0], ln);
     uint32_t* ra = cluster.map_shared_rank(&sh.a[q][0], ln);
     uint32_t* rb = cluster.map_shared_rank(&sh.b[q][0], ln);
-    if (live) {
-      if (nw) {
-        const unsigned long long pe = cursor + (uint32_t(excl >> 42) & 0x1FFFFFu);
-        if (pe + nw <= a.ecap[l]) put_words(a.emit[l] + pe, nw, e0, e1, e2, x1, x);
+    {
+      uint32_t zat = uint32_t(excl) & 0x1FFFFFu;
+      uint32_t oat = tz + (uint32_t(excl >> 21) & 0x1FFFFFu);
+      unsigned long long pe = cursor + (uint32_t(excl >> 42) & 0x1FFFFFu);
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (nw[j]) {
+          if (pe + nw[j] <= a.ecap[l]) put_words(a.emit[l] + pe, nw[j], e0[j], e1[j], e2[j], x1[j], x0[j] + x1[j]);
+          pe += nw[j];
+        }
+        if (fz >> j & 1u) { rs[zat] = cs0[j]; ra[zat] = ca[j]; rb[zat] = cb[j]; ++zat; }
+        if (fo >> j & 1u) { rs[oat] = cs1[j]; ra[oat] = oa[j]; rb[oat] = ob[j]; ++oat; }
       }
-      if (fz) { const uint32_t at = uint32_t(excl) & 0x1FFFFFu; rs[at] = s0; ra[at] = za0; rb[at] = za1; }
-      if (fo) { const uint32_t at = tz + (uint32_t(excl >> 21) & 0x1FFFFFu); rs[at] = a.C[ln] + s1; ra[at] = oa0; rb[at] = oa1; }
     }
     cursor += te;
     if (tid == 0) {
@@ -324,7 +368,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_n
   {
     const int opar = round & 1;
     const uint32_t cz = sh.cz[p], co = sh.co[p];
-    for (uint32_t t = tid; t < cz + co; t += NR_THREADS) {
+    for (uint32_t t = tid; t < cz + co; t += THREADS) {
       const uint32_t idx = t < cz ? t : a.cap - 1 - (t - cz);
       a.fs[opar][l][idx] = sh.s[p][t];
       a.fa[opar][l][idx] = sh.a[p][t];
@@ -346,12 +390,175 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(NR_THREADS, 1) cse_n
 }
 
 // ---------------------------------------------------------------------------------
+// tiny mode: the last thousands of rounds carry a handful of nodes per level (one per long
+// repeat that is still being told apart).  ONE CTA, warp w = level w, at most 32 nodes per level:
+// ballots instead of block scans, __syncthreads instead of a cluster barrier -- a round costs
+// little more than the latency of its three rank-word loads.
+// ---------------------------------------------------------------------------------
+constexpr int TN_ITEMS = 1;                       // nodes per lane (4 was measured: 1.25 us per round instead of 0.84, no net gain)
+constexpr int TN_CAP = 32 * TN_ITEMS;             // nodes per level
+constexpr uint32_t kTinyEnter = TN_CAP / 4, kTinyLeave = TN_CAP / 2;    // <= 2 children per node: the next round fits
+
+struct TinyShared {
+  uint32_t s[2][8][TN_CAP], a[2][8][TN_CAP], b[2][8][TN_CAP];
+  uint32_t cz[2][8], co[2][8];
+  unsigned long long emitted[2][8];
+};
+
+__global__ void __launch_bounds__(256, 1) cse_tiny_kernel(CseArgs a) {
+  __shared__ TinyShared sh;
+  const unsigned tid = threadIdx.x, lane = tid & 31;
+  const int l = int(tid >> 5);                       // level handled by this warp
+  const int ln = (l + 1) & 7;
+  CseDeviceState* S = a.st;
+  const uint64_t* __restrict__ R = a.ranks[l];
+  const uint32_t maxw = max_words(a);
+  const uint32_t one_base = a.C[ln];
+
+  uint32_t round = S->round;
+  {
+    const int gpar = round & 1;
+    const uint32_t cz = S->cnt[gpar][l][0], co = S->cnt[gpar][l][1];
+    if (lane == 0) { sh.cz[0][l] = cz; sh.co[0][l] = co; sh.emitted[0][l] = S->emitted[gpar][l]; }
+    for (uint32_t t = lane; t < cz + co && t < uint32_t(TN_CAP); t += 32) {
+      const uint32_t idx = t < cz ? t : a.cap - 1 - (t - cz);
+      sh.s[0][l][t] = a.fs[gpar][l][idx];
+      sh.a[0][l][t] = a.fa[gpar][l][idx];
+      sh.b[0][l][t] = a.fb[gpar][l][idx];
+    }
+  }
+  unsigned long long cursor = S->emitted[round & 1][l];
+  unsigned long long visits = 0, peak = 0;
+  int p = 0;
+  __syncthreads();
+
+  uint32_t status;
+  for (;;) {
+    {   // every thread takes the same decision from the same shared values
+      uint32_t total = 0, widest = 0, drain = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t cnt = sh.cz[p][k] + sh.co[p][k];
+        total += cnt;
+        widest = max(widest, cnt);
+        if (sh.emitted[p][k] + (unsigned long long)cnt * maxw > a.ecap[k]) drain = 1;
+      }
+      status = total == 0 ? kCseDone
+             : round >= a.round_limit ? kCseRunaway
+             : widest > kTinyLeave ? kCseGoWide
+             : drain ? kCseDrain : kCseRunning;
+      if (status != kCseRunning) break;
+      visits += total;
+      peak = max(peak, (unsigned long long)total);
+    }
+    const uint32_t cnt = sh.cz[p][l] + sh.co[p][l];
+    // lane owns nodes lane * TN_ITEMS + j: consecutive nodes, so offsets are one warp scan of per-lane sums
+    uint32_t s[TN_ITEMS], x0[TN_ITEMS], x1[TN_ITEMS];
+    uint64_t wa[TN_ITEMS], wb[TN_ITEMS], wc[TN_ITEMS];
+#pragma unroll
+    for (int j = 0; j < TN_ITEMS; ++j) {
+      const uint32_t t = lane * TN_ITEMS + j;
+      const bool live = t < cnt;
+      s[j] = live ? sh.s[p][l][t] : 0u;
+      x0[j] = live ? sh.a[p][l][t] : 0u;
+      x1[j] = live ? sh.b[p][l][t] : 0u;
+      if (live) {
+        wa[j] = __ldg(R + (s[j] >> 5));
+        wb[j] = __ldg(R + ((s[j] + x0[j] + x1[j]) >> 5));
+        wc[j] = __ldg(R + ((s[j] + x0[j]) >> 5));
+      } else { wa[j] = wb[j] = wc[j] = 0; }
+    }
+    uint32_t fz = 0, fo = 0, nwsum = 0;
+    uint32_t cs0[TN_ITEMS], ca[TN_ITEMS], cb[TN_ITEMS], cs1[TN_ITEMS], oa[TN_ITEMS], ob[TN_ITEMS];
+    uint32_t e0[TN_ITEMS], e1[TN_ITEMS], e2[TN_ITEMS], nw[TN_ITEMS];
+#pragma unroll
+    for (int j = 0; j < TN_ITEMS; ++j) {
+      cs0[j] = ca[j] = cb[j] = cs1[j] = oa[j] = ob[j] = e0[j] = e1[j] = e2[j] = nw[j] = 0;
+      if (lane * TN_ITEMS + j < cnt) {
+        const uint32_t x = x0[j] + x1[j];
+        const uint32_t s1 = rank1_word(wa[j], s[j]);
+        const uint32_t c1 = rank1_word(wb[j], s[j] + x) - s1;
+        const uint32_t s0 = s[j] - s1;
+        const uint32_t z0 = (s[j] + x0[j] - rank1_word(wc[j], s[j] + x0[j])) - s0;
+        cs0[j] = s0;
+        cs1[j] = one_base + s1;
+        if (c1 == 0) { fz |= 1u << j; ca[j] = x0[j]; cb[j] = x1[j]; }
+        else if (c1 == x) { fo |= 1u << j; oa[j] = x0[j]; ob[j] = x1[j]; }
+        else {
+          const uint32_t c0 = x - c1;
+          const uint32_t lo = x0[j] > c1 ? x0[j] - c1 : 0u;
+          const uint32_t hi = x0[j] - (c1 > x1[j] ? c1 - x1[j] : 0u);
+          const uint32_t z1 = c0 - z0, o1 = x1[j] - z1, o0c = c1 - o1;
+          if (hi != lo) nw[j] = count_words(a, l, z0 - lo, hi - lo + 1, c0, x1[j], x, e0[j], e1[j], e2[j]);   // bce.cpp:1302
+          if (z0 && z1) { fz |= 1u << j; ca[j] = z0; cb[j] = z1; }
+          if (o0c && o1) { fo |= 1u << j; oa[j] = o0c; ob[j] = o1; }
+        }
+        nwsum += nw[j];
+      }
+    }
+    // packed inclusive warp scan: zero-children | one-children << 8 | emitted words << 16
+    const uint32_t mine = uint32_t(__popc(fz)) | (uint32_t(__popc(fo)) << 8) | (nwsum << 16);
+    uint32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= unsigned(d)) inc += o;
+    }
+    const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+    const uint32_t tz = tot & 255u, to = (tot >> 8) & 255u, te = tot >> 16;
+    const uint32_t excl = inc - mine;
+    const int q = p ^ 1;
+    {
+      uint32_t zat = excl & 255u, oat = tz + ((excl >> 8) & 255u);
+      unsigned long long pe = cursor + (excl >> 16);
+#pragma unroll
+      for (int j = 0; j < TN_ITEMS; ++j) {
+        if (nw[j]) {
+          if (pe + nw[j] <= a.ecap[l]) put_words(a.emit[l] + pe, nw[j], e0[j], e1[j], e2[j], x1[j], x0[j] + x1[j]);
+          pe += nw[j];
+        }
+        if (fz >> j & 1u) { sh.s[q][ln][zat] = cs0[j]; sh.a[q][ln][zat] = ca[j]; sh.b[q][ln][zat] = cb[j]; ++zat; }
+        if (fo >> j & 1u) { sh.s[q][ln][oat] = cs1[j]; sh.a[q][ln][oat] = oa[j]; sh.b[q][ln][oat] = ob[j]; ++oat; }
+      }
+    }
+    cursor += te;
+    if (lane == 0) { sh.cz[q][ln] = tz; sh.co[q][ln] = to; sh.emitted[q][l] = cursor; }
+    __syncthreads();
+    p = q;
+    ++round;
+  }
+
+  {   // hand the state back in the wide layout
+    const int opar = round & 1;
+    const uint32_t cz = sh.cz[p][l], co = sh.co[p][l];
+    for (uint32_t t = lane; t < cz + co; t += 32) {
+      const uint32_t idx = t < cz ? t : a.cap - 1 - (t - cz);
+      a.fs[opar][l][idx] = sh.s[p][l][t];
+      a.fa[opar][l][idx] = sh.a[p][l][t];
+      a.fb[opar][l][idx] = sh.b[p][l][t];
+    }
+    if (lane == 0) {
+      S->cnt[opar][l][0] = cz;
+      S->cnt[opar][l][1] = co;
+      S->emitted[opar][l] = cursor;
+      if (l == 0) {
+        S->round = round;
+        S->status = status;
+        S->visits += visits;
+        if (peak > S->peak_frontier) S->peak_frontier = peak;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
 struct CseHost {
   CseArgs args;
   uint32_t n = 0;
-  bool narrow = true;                    // which kernel runs next (the root frontier is narrow)
+  int narrow = 1;                        // which kernel runs next: 0 wide, 1 cluster kernel <1024, 1>, 8 cluster kernel <512, 8>, 2 one-CTA kernel
+                                         // (the root frontier is narrow)
   uint32_t last_round = 0;
   // wide kernel variants: [0] = 2 nodes per thread (512-node tiles), [1] = 4 (1024-node tiles)
   const void* var_fn[2] = {nullptr, nullptr};
@@ -370,6 +577,8 @@ struct CseHost {
   int pending_set = 0;
   size_t pending_cnt[8] = {};
   int pinned_flip = 0;
+  bool use_medium = false;               // the <512, 8> cluster kernel is available
+  int last_grid = 0;                     // grid size of the previous wide launch (0 = none since cse_begin)
   bool tail_cut = false;                 // hosted emission: the batch was already cut where the frontier collapsed
   bool finished = false;                 // the level loop terminated
 };
@@ -443,11 +652,27 @@ int cse_begin(Ctx* c, uint32_t n) {
   a.max_nodes = ~0ull;
   a.st = reinterpret_cast<CseDeviceState*>(c->small.as<char>() + kSmallCse);
   static_assert(sizeof(CseDeviceState) <= 1024, "state must fit its slot in Ctx::small");
-  H->narrow = a.use_narrow != 0;
+  H->narrow = a.use_narrow ? 1 : 0;
+  H->use_medium = a.use_narrow && !env_size("BCE_GPU_NO_MEDIUM", 0);
+  a.use_tiny = (a.use_narrow && !env_size("BCE_GPU_NO_TINY", 0)) ? 1u : 0u;
+  a.tiny_enter = kTinyEnter;
+  if (a.use_tiny) H->narrow = 2;         // the roots are one node per level
+  a.narrow_enter = H->use_medium ? kMediumEnter : kNarrowEnter;
+  {
+    static bool attr_done = false;
+    if (!attr_done) {
+      BCE_CUDA(c, cudaFuncSetAttribute(cse_narrow_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(sizeof(NarrowShared<1024, 1>))));
+      BCE_CUDA(c, cudaFuncSetAttribute(cse_narrow_kernel<NM_THREADS, NM_K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       int(sizeof(NarrowShared<NM_THREADS, NM_K>))));
+      attr_done = true;
+    }
+  }
   H->last_round = 0;
   H->known_nodes = 0;
   H->pending = H->pending_done = H->finished = false;
   H->tail_cut = false;
+  H->last_grid = 0;
   H->pinned_flip = 0;                        // single-batch runs always land in the same pinned buffer
   const int items = int(env_size("BCE_GPU_CSE_ITEMS", 0));
   H->fixed_items = (items == 2 || items == 4) ? items : 0;
@@ -492,7 +717,7 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
   bool cut = false;                      // batch ended by the host between two kernels
   for (int hops = 0;; ++hops) {
     if (hops > 100000) { set_error(c, "cse: wide/narrow ping-pong"); return BCE_GPU_E_INTERNAL; }
-    const bool was_narrow = H->narrow;
+    const bool was_narrow = H->narrow != 0;
     BCE_CUDA(c, cudaEventRecord(c->ev[0], st));
     {   // timing experiments (BCE_GPU_CSE_DBG_ROUND / _FLAGS): run one chosen round with parts off
       const uint32_t dbg_round = uint32_t(env_size("BCE_GPU_CSE_DBG_ROUND", 0));
@@ -503,8 +728,14 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
         else if (H->last_round == dbg_round) { H->args.max_rounds = 1; H->args.dbg = uint32_t(env_size("BCE_GPU_CSE_DBG_FLAGS", 0)); }
       }
     }
-    if (H->narrow) {
-      cse_narrow_kernel<<<8, NR_THREADS, 0, st>>>(H->args);
+    if (H->narrow == 2) {
+      cse_tiny_kernel<<<1, 256, 0, st>>>(H->args);
+      BCE_CUDA(c, cudaGetLastError());
+    } else if (H->narrow == 1) {
+      cse_narrow_kernel<1024, 1><<<8, 1024, sizeof(NarrowShared<1024, 1>), st>>>(H->args);
+      BCE_CUDA(c, cudaGetLastError());
+    } else if (H->narrow) {
+      cse_narrow_kernel<NM_THREADS, NM_K><<<8, NM_THREADS, sizeof(NarrowShared<NM_THREADS, NM_K>), st>>>(H->args);
       BCE_CUDA(c, cudaGetLastError());
     } else {
       // 1024-node tiles while the frontier is huge, 512-node tiles below (more CTAs per round)
@@ -512,13 +743,30 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
       H->args.min_nodes = 0;
       H->args.max_nodes = ~0ull;
       int v;
-      if (H->fixed_items) v = H->fixed_items == 4 ? 1 : 0;
+      int grid;
+      if (H->fixed_items) { v = H->fixed_items == 4 ? 1 : 0; grid = H->var_grid[v]; }
       else {
         v = H->known_nodes >= kBig ? 1 : 0;
-        if (v) H->args.min_nodes = kLeaveBig; else H->args.max_nodes = kLeaveSmall;
+        grid = H->var_grid[v];
+        if (v) H->args.min_nodes = kLeaveBig;
+        else {
+          H->args.max_nodes = kLeaveSmall;
+          // A frontier of a few thousand nodes is a handful of tiles: what a round costs then is the
+          // grid barrier, and that grows with the number of CTAs that have to arrive.
+          const unsigned long long small_below = env_size("BCE_GPU_CSE_SMALL_NODES", 0);
+          const int small_grid = int(env_size("BCE_GPU_CSE_SMALL_GRID", 0));
+          if (small_grid > 0 && small_grid < grid) {
+            if (H->known_nodes < small_below) { grid = small_grid; H->args.max_nodes = 2 * small_below; }
+            else H->args.min_nodes = small_below / 2;
+          }
+        }
+      }
+      if (grid != H->last_grid) {
+        if (H->last_grid) { cse_reset_barrier_kernel<<<1, 1, 0, st>>>(H->args.st); c->stats.gpu_launches++; }
+        H->last_grid = grid;
       }
       void* kargs[] = {&H->args};
-      BCE_CUDA(c, cudaLaunchCooperativeKernel(H->var_fn[v], dim3(H->var_grid[v]), dim3(CS_THREADS), kargs,
+      BCE_CUDA(c, cudaLaunchCooperativeKernel(H->var_fn[v], dim3(grid), dim3(CS_THREADS), kargs,
                                               H->var_smem[v], st));
     }
     c->stats.gpu_launches++;
@@ -541,7 +789,17 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
     if (h_state->err) break;
     if (h_state->status == kCseRunning && H->args.max_rounds != 0x7FFFFFFFu) continue;   // stopped on request
     if (h_state->status == kCseGoWide || h_state->status == kCseGoNarrow) {
-      H->narrow = h_state->status == kCseGoNarrow;
+      {   // the widest level decides which kernel takes the next rounds
+        const int par = h_state->round & 1;
+        uint32_t widest = 0;
+        for (int l = 0; l < 8; ++l) widest = std::max(widest, h_state->cnt[par][l][0] + h_state->cnt[par][l][1]);
+        H->narrow = !H->args.use_narrow ? 0
+                  : (H->args.use_tiny && widest <= kTinyEnter) ? 2
+                  : widest <= kNarrowEnter ? 1
+                  : (H->use_medium && widest <= kMediumEnter) ? NM_K : 0;
+        // the one-node-per-thread kernel asked to leave (> 512) or the wide one asked to hand over (<= narrow_enter):
+        // both are consistent with the choice above, so no kernel is relaunched just to bounce back
+      }
       // Hosted emission: when the frontier has collapsed, what follows is thousands of short rounds
       // that emit little.  End the batch here so that its copy to the host runs under that tail
       // instead of after it.

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
       s_flags[0] = t;
       s_flags[1] = nodes == 0 ? kCseDone
                  : round >= a.round_limit ? kCseRunaway
-                 : (a.use_narrow && widest <= kNarrowEnter) ? kCseGoNarrow
+                 : (a.use_narrow && widest <= a.narrow_enter) ? kCseGoNarrow
                  : (nodes < a.min_nodes || nodes > a.max_nodes) ? kCseGoWide      // host picks the other tile size
                  : drain ? kCseDrain : kCseRunning;
       if (blockIdx.x == 0 && s_flags[1] == kCseRunning && rounds_done < a.max_rounds) {

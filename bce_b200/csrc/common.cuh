@@ -133,7 +133,10 @@ __device__ __forceinline__ uint32_t lookback_serial(uint64_t* desc, uint32_t str
     return 0;
   }
   desc_store(desc + size_t(tile) * stride, desc_pack(tag, kDescAgg, agg));
-  constexpr int kBatch = 4;
+  #ifndef BCE_LB_BATCH
+#define BCE_LB_BATCH 2
+#endif
+  constexpr int kBatch = BCE_LB_BATCH;
   uint32_t excl = 0;
   uint32_t t = tile;                      // next predecessor to look at is t - 1
   bool done = false;

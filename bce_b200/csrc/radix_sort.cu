@@ -9,6 +9,7 @@
 // Digit histograms for all passes of one sort come from one extra read of the keys.
 //
 // HBM traffic per pass: read 12 B + write 12 B per element  (24 m P_r).
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -82,7 +83,10 @@ struct RadixPass {
   uint32_t dbg;           // timing experiments only: 1 = skip the chained scan (output order wrong)
 };
 
-template <int RS_THREADS, int RS_ITEMS, int MIN_CTAS>
+// BALLOT picks how a warp finds the lanes that hold the same digit: MATCH.ANY costs time in proportion to the
+// number of different digits in the warp, eight ballots cost the same whatever the digits are.  The host
+// chooses per pass from the digit histogram (see radix_sort_pairs).
+template <int RS_THREADS, int RS_ITEMS, int MIN_CTAS, bool BALLOT = false>
 __global__ void __launch_bounds__(RS_THREADS, MIN_CTAS) radix_onesweep_kernel(RadixPass p) {
   constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
   constexpr int RS_WARPS = RS_THREADS / 32;
@@ -119,7 +123,17 @@ __global__ void __launch_bounds__(RS_THREADS, MIN_CTAS) radix_onesweep_kernel(Ra
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
     uint32_t d = uint32_t(key[k] >> p.shift) & 255u;
-    unsigned peers = __match_any_sync(0xffffffffu, d);
+unsigned peers;
+    if (BALLOT) {
+      peers = 0xffffffffu;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const unsigned v = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+        peers &= ((d >> b) & 1u) ? v : ~v;
+      }
+    } else {
+      peers = __match_any_sync(0xffffffffu, d);
+    }
     unsigned leader = __ffs(peers) - 1;
     uint32_t before = 0;
     if (lane == leader) {
@@ -179,6 +193,7 @@ __global__ void __launch_bounds__(RS_THREADS, MIN_CTAS) radix_onesweep_kernel(Ra
 namespace bce {
 
 static uint32_t g_radix_dbg = 0;
+static double env_size_d(const char* name, double dflt) { const char* v = getenv(name); return v && *v ? atof(v) : dflt; }
 void byte_hist_launch(Ctx* c, const uint8_t* L, uint32_t n, uint32_t* d_hist);   // wavelet.cu
 
 int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uint32_t* valB,
@@ -256,7 +271,7 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
   uint64_t* kin = keyA; uint64_t* kout = keyB;
   uint32_t* vin = valA; uint32_t* vout = valB;
   // kernel configuration (threads x keys per thread); BCE_GPU_RADIX_CFG picks one for experiments
-  struct Cfg { void (*fn)(RadixPass); int threads, items; };
+  struct Cfg { void (*fn)(RadixPass); int threads, items; void (*fn_ballot)(RadixPass); };
   static const Cfg cfgs[] = {
     {radix_onesweep_kernel<256, 12, 3>, 256, 12},
     {radix_onesweep_kernel<256, 16, 3>, 256, 16},
@@ -265,7 +280,7 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
     {radix_onesweep_kernel<256, 8, 4>, 256, 8},
     {radix_onesweep_kernel<512, 12, 1>, 512, 12},
     {radix_onesweep_kernel<256, 20, 3>, 256, 20},
-    {radix_onesweep_kernel<256, 24, 2>, 256, 24},
+    {radix_onesweep_kernel<256, 24, 2>, 256, 24, radix_onesweep_kernel<256, 24, 2, true>},
     {radix_onesweep_kernel<256, 28, 2>, 256, 28},
     {radix_onesweep_kernel<256, 32, 2>, 256, 32},
     {radix_onesweep_kernel<384, 16, 2>, 384, 16},
@@ -279,6 +294,7 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
   const size_t rs_smem = size_t(RS_TILE) * 12 + size_t(cfg.threads / 32) * 1024;
   static bool attr_set[12] = {};
   if (!attr_set[which_cfg]) {
+    if (cfg.fn_ballot) BCE_CUDA(c, cudaFuncSetAttribute(cfg.fn_ballot, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem)));
     BCE_CUDA(c, cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem)));
     attr_set[which_cfg] = true;
   }
@@ -301,6 +317,7 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
     d_chist = c->radix_tmp.as<uint32_t>();
     d_offs = d_chist + size_t(chunks) * 256;
   }
+  const double ballot_above = double(env_size_d("BCE_GPU_RADIX_BALLOT_ABOVE", 24.0));
   int ran = 0;
   for (int p = 0; p < npass; ++p) {
     if (!run[p]) continue;
@@ -324,7 +341,19 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
       radix_downsweep_kernel<<<chunks, RD_THREADS, 0, c->stream>>>(dn);
       c->stats.gpu_launches += 2;
     } else {
-      cfg.fn<<<tiles, RS_THREADS, rs_smem, c->stream>>>(a);
+      // expected number of different digits among 32 keys drawn from this pass's histogram
+      double distinct = 0;
+      for (int d = 0; d < 256; ++d) {
+        const double q = double(h_hist[p * 256 + d]) / double(m);
+        if (q > 0) distinct += 1.0 - pow(1.0 - q, 32.0);
+      }
+      // keys that are text windows arrive sorted by the bytes that follow: after the first passes a
+      // warp's keys share their context and with it, mostly, the digit
+      const bool context_sorted = window_text && ran >= 2;
+      const char* force = getenv("BCE_GPU_RADIX_RANK");          // experiments: "match" / "ballot"
+      bool ballot = cfg.fn_ballot && distinct > ballot_above && !context_sorted;
+      if (force && cfg.fn_ballot) ballot = force[0] == 'b';
+      (ballot ? cfg.fn_ballot : cfg.fn)<<<tiles, RS_THREADS, rs_smem, c->stream>>>(a);
     }
     if (timed) { cudaEventRecord(c->pass_ev[c->pass_ev_n + 1], c->stream); c->pass_ev_n += 2; }
     c->stats.gpu_launches++;

@@ -70,8 +70,10 @@ __global__ void __launch_bounds__(256) pack_keys_kernel(const uint8_t* __restric
 // K3: re-rank + stable compaction of the rotations that are still tied
 // ---------------------------------------------------------------------------------
 constexpr int RR_THREADS = 256;
-constexpr int RR_ITEMS = 16;
-constexpr int RR_TILE = RR_THREADS * RR_ITEMS;
+constexpr int RR_WARPS = RR_THREADS / 32;
+constexpr int RR_ROWS = 8;                          // rows of 32 consecutive slots per warp
+constexpr int RR_WCHUNK = 32 * RR_ROWS;             // slots per warp
+constexpr int RR_TILE = RR_WARPS * RR_WCHUNK;       // 2048 slots per tile
 
 struct RerankArgs {
   const uint64_t* key;      // sorted keys of the working set
@@ -93,9 +95,14 @@ struct RerankArgs {
   uint32_t dbg;             // timing experiments only: 1 no rank scatter, 2 no SA write, 4 no compaction writes
 };
 
+// Lane l of a warp holds slots wbase + 32 k + l (k = 0 .. RR_ROWS-1): every load and store of a row is
+// one coalesced access, a slot's neighbours sit in the neighbouring lanes, and everything positional --
+// the governing group head of a slot, how many survivors and surviving heads precede it -- comes from
+// ballot masks of the rows (one 32-bit word per row, the same in all lanes) with popc / clz.
+// (A first version gave every thread 8-16 consecutive slots: ncu showed 22 sectors per store request
+// and the L1 as the busiest unit.)
 __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
-  __shared__ uint32_t s_scan32[RR_THREADS / 32];
-  __shared__ uint64_t s_scan64[RR_THREADS / 32];
+  __shared__ uint32_t s_whead[RR_WARPS], s_wsurv[RR_WARPS], s_wshead[RR_WARPS];
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_carry[3];
 
@@ -103,143 +110,111 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
   if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
-  const uint32_t q0 = tile * RR_TILE + tid * RR_ITEMS;
+  const uint32_t wbase = tile * RR_TILE + warp * RR_WCHUNK;      // < 2^32: m < 2^31
 
-  uint64_t key[RR_ITEMS + 2];     // key[0] = predecessor, key[ITEMS+1] = successor
-  uint32_t idx[RR_ITEMS], sap[RR_ITEMS];
-  const bool full = tile * RR_TILE + RR_TILE <= a.m;       // whole tile inside the working set: 16-byte accesses
-  if (full) {
-    const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(a.key + q0);
+  uint64_t key[RR_ROWS];
+  uint32_t idx[RR_ROWS], sap[RR_ROWS];
 #pragma unroll
-    for (int j = 0; j < RR_ITEMS / 2; ++j) {
-      const ulonglong2 v = kp[j];
-      key[2 * j + 1] = v.x;
-      key[2 * j + 2] = v.y;
-    }
-    const uint4* ip = reinterpret_cast<const uint4*>(a.idx + q0);
-#pragma unroll
-    for (int j = 0; j < RR_ITEMS / 4; ++j) {
-      const uint4 v = ip[j];
-      idx[4 * j] = v.x; idx[4 * j + 1] = v.y; idx[4 * j + 2] = v.z; idx[4 * j + 3] = v.w;
-    }
-    if (a.sapos) {
-      const uint4* sp = reinterpret_cast<const uint4*>(a.sapos + q0);
-#pragma unroll
-      for (int j = 0; j < RR_ITEMS / 4; ++j) {
-        const uint4 v = sp[j];
-        sap[4 * j] = v.x; sap[4 * j + 1] = v.y; sap[4 * j + 2] = v.z; sap[4 * j + 3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < RR_ITEMS; ++j) sap[j] = q0 + j;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < RR_ITEMS; ++j) {
-      uint32_t q = q0 + j;
-      bool in = q < a.m;
-      key[j + 1] = in ? a.key[q] : 0;
-      idx[j] = in ? a.idx[q] : 0;
-      sap[j] = in ? (a.sapos ? a.sapos[q] : q) : 0;
-    }
+  for (int k = 0; k < RR_ROWS; ++k) {
+    const uint32_t q = wbase + k * 32 + lane;
+    const bool in = q < a.m;
+    key[k] = in ? a.key[q] : 0;
+    idx[k] = in ? a.idx[q] : 0;
+    sap[k] = in ? (a.sapos ? a.sapos[q] : q) : 0;
   }
-  key[0] = (q0 > 0 && q0 - 1 < a.m) ? a.key[q0 - 1] : 0;
-  key[RR_ITEMS + 1] = (q0 + RR_ITEMS < a.m) ? a.key[q0 + RR_ITEMS] : 0;
+  // the keys just outside the warp's chunk (uniform loads)
+  const uint64_t key_before = (wbase > 0 && wbase - 1 < a.m) ? a.key[wbase - 1] : 0;
+  const uint64_t key_after = (wbase + RR_WCHUNK < a.m) ? a.key[wbase + RR_WCHUNK] : 0;
 
-  // head = first slot of a (new) group; lone = group of one
-  uint32_t head_bits = 0, surv_bits = 0, shead_bits = 0, lone_bits = 0;
-  uint32_t last_head = 0;            // (slot + 1) of the most recent head in this thread
-  uint32_t nsurv = 0, nshead = 0;
+  // head = first slot of a (new) group
+  uint32_t H[RR_ROWS];
 #pragma unroll
-  for (int j = 0; j < RR_ITEMS; ++j) {
-    uint32_t q = q0 + j;
-    if (q < a.m) {
-      bool head = (q == 0) || key[j + 1] != key[j];
-      bool next_head = (q + 1 == a.m) || key[j + 2] != key[j + 1];
-      bool lone = head && next_head;
-      if (head) { head_bits |= 1u << j; last_head = q + 1; }
-      if (!lone) { surv_bits |= 1u << j; ++nsurv; } else lone_bits |= 1u << j;
-      if (head && !lone) { shead_bits |= 1u << j; ++nshead; }
-    }
+  for (int k = 0; k < RR_ROWS; ++k) {
+    const uint32_t q = wbase + k * 32 + lane;
+    const uint64_t up = __shfl_up_sync(0xffffffffu, key[k], 1);
+    const uint64_t wrap = k ? __shfl_sync(0xffffffffu, key[k ? k - 1 : 0], 31) : key_before;
+    const uint64_t prev = lane ? up : wrap;
+    H[k] = __ballot_sync(0xffffffffu, q < a.m && (q == 0 || key[k] != prev));
   }
-
-  // (1) block-wide inclusive max-scan of last_head  ->  head slot for every element
-  uint32_t inc = last_head;
+  // is the slot after the warp's last one a head (or the end)?
+  const bool after_is_head = (wbase + RR_WCHUNK >= a.m) ||
+                             (key_after != __shfl_sync(0xffffffffu, key[RR_ROWS - 1], 31));
+  // lone = a group of one: head whose successor is a head (or the end of the working set)
+  auto masks = [&](int k, uint32_t& S, uint32_t& SH, uint32_t& L) {
+    const uint32_t q = wbase + k * 32 + lane;
+    const bool in = q < a.m;
+    const bool head = (H[k] >> lane) & 1u;
+    const bool nh = (q + 1 >= a.m) ? true
+                  : lane < 31 ? ((H[k] >> (lane + 1)) & 1u)
+                  : k + 1 < RR_ROWS ? (H[k + 1 < RR_ROWS ? k + 1 : k] & 1u) : after_is_head;
+    const bool lone = head && nh;
+    L = __ballot_sync(0xffffffffu, in && lone);
+    S = __ballot_sync(0xffffffffu, in && !lone);
+    SH = __ballot_sync(0xffffffffu, in && head && !lone);
+  };
+  uint32_t wsurv = 0, wshead = 0, whead = 0;          // this warp's survivors, surviving heads, (slot + 1) of its last head
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-    if (lane >= unsigned(d)) inc = max(inc, o);
+  for (int k = 0; k < RR_ROWS; ++k) {
+    uint32_t S, SH, L;
+    masks(k, S, SH, L);
+    wsurv += __popc(S);
+    wshead += __popc(SH);
+    if (H[k]) whead = wbase + k * 32 + (31 - __clz(H[k])) + 1;
   }
-  if (lane == 31) s_scan32[warp] = inc;
-  // (2) block-wide exclusive sum-scan of (survivors, surviving heads) packed in 64 bits
-  uint64_t packed = uint64_t(nsurv) | (uint64_t(nshead) << 32);
-  uint64_t inc64 = packed;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    uint64_t o = __shfl_up_sync(0xffffffffu, inc64, d);
-    if (lane >= unsigned(d)) inc64 += o;
-  }
-  if (lane == 31) s_scan64[warp] = inc64;
+  if (lane == 0) { s_whead[warp] = whead; s_wsurv[warp] = wsurv; s_wshead[warp] = wshead; }
   __syncthreads();
-  uint32_t carry_head = 0, tile_head = 0;
-  uint64_t woff = 0, tile_sum = 0;
+  uint32_t head_before = 0, surv_before = 0, shead_before = 0, tile_head = 0, tile_surv = 0, tile_shead = 0;
 #pragma unroll
-  for (int w = 0; w < RR_THREADS / 32; ++w) {
-    uint32_t hv = s_scan32[w];
-    uint64_t sv = s_scan64[w];
-    if (unsigned(w) < warp) { carry_head = max(carry_head, hv); woff += sv; }
+  for (int w = 0; w < RR_WARPS; ++w) {
+    const uint32_t hv = s_whead[w], sv = s_wsurv[w], shv = s_wshead[w];
+    if (unsigned(w) < warp) { head_before = max(head_before, hv); surv_before += sv; shead_before += shv; }
     tile_head = max(tile_head, hv);
-    tile_sum += sv;
+    tile_surv += sv;
+    tile_shead += shv;
   }
-  // exclusive (over threads) last head before this thread's first slot
-  uint32_t prev_inc = __shfl_up_sync(0xffffffffu, inc, 1);
-  uint32_t head_before = max(carry_head, lane ? prev_inc : 0u);
-  uint64_t excl64 = woff + inc64 - packed;
-
-  // (3) carries across tiles: three independent chained scans, one warp each
+  // carries across tiles: three independent chained scans, one warp each
   if (warp < 3) {
     uint64_t* d = a.desc + size_t(warp) * a.tiles;
     uint32_t v;
     if (warp == 0) v = lookback_warp_max(d, tile, 0u, a.tag, tile_head, a.err);
-    else if (warp == 1) v = lookback_warp(d, tile, 0u, a.tag, uint32_t(tile_sum), a.err);
-    else v = lookback_warp(d, tile, 0u, a.tag, uint32_t(tile_sum >> 32), a.err);
+    else if (warp == 1) v = lookback_warp(d, tile, 0u, a.tag, tile_surv, a.err);
+    else v = lookback_warp(d, tile, 0u, a.tag, tile_shead, a.err);
     if (lane == 0) s_carry[warp] = v;
   }
   __syncthreads();
-  const uint32_t tile_head_carry = s_carry[0];
-  uint32_t out_at = s_carry[1] + uint32_t(excl64);
-  uint32_t gd_run = s_carry[2] + uint32_t(excl64 >> 32);    // surviving heads before this thread
+  uint32_t run_head = max(head_before, s_carry[0]);     // (slot + 1) of the last head before the current row
+  uint32_t out_at = s_carry[1] + surv_before;           // survivors before the current row
+  uint32_t gd_run = s_carry[2] + shead_before;          // surviving heads before the current row
 
-  uint32_t cur_head = max(head_before, tile_head_carry);      // (slot+1) of the governing head
-  uint64_t pr[RR_ITEMS];
 #pragma unroll
-  for (int j = 0; j < RR_ITEMS; ++j) {
-    uint32_t q = q0 + j;
-    if (q >= a.m) break;
-    if (head_bits >> j & 1u) cur_head = q + 1;
-    if (shead_bits >> j & 1u) ++gd_run;
-    // slots of one group are consecutive in SA, so the head's SA position is sap - distance
-    uint32_t rank = sap[j] - (q - (cur_head - 1));
-    // SA is final for a slot once its group is a single rotation; tied slots come back next round
-    if ((lone_bits >> j & 1u) && !(a.dbg & 2u)) a.sa[sap[j]] = idx[j];
-    pr[j] = (uint64_t(idx[j]) << 32) | rank;
-    if (a.pairs) { if (!full) a.pairs[q] = pr[j]; }
-    else if (!(a.dbg & 1u)) a.rnk[idx[j]] = rank;
-    if ((surv_bits >> j & 1u) && !(a.dbg & 4u)) {
-      a.idx_out[out_at] = idx[j];
-      a.sapos_out[out_at] = sap[j];
-      a.gd_out[out_at] = gd_run - 1;
-      ++out_at;
+  for (int k = 0; k < RR_ROWS; ++k) {
+    const uint32_t q = wbase + k * 32 + lane;
+    uint32_t S, SH, L;
+    masks(k, S, SH, L);
+    const uint32_t le = lanemask_lt() | (1u << lane);
+    const uint32_t hm = H[k] & le;
+    const uint32_t my_head = hm ? wbase + k * 32 + (31 - __clz(hm)) + 1 : run_head;
+    if (q < a.m) {
+      // slots of one group are consecutive in SA, so the head's SA position is sap - distance
+      const uint32_t rank = sap[k] - (q - (my_head - 1));
+      // SA is final for a slot once its group is a single rotation; tied slots come back next round
+      if (((L >> lane) & 1u) && !(a.dbg & 2u)) a.sa[sap[k]] = idx[k];
+      if (a.pairs) a.pairs[q] = (uint64_t(idx[k]) << 32) | rank;
+      else if (!(a.dbg & 1u)) a.rnk[idx[k]] = rank;
+      if (((S >> lane) & 1u) && !(a.dbg & 4u)) {
+        const uint32_t at = out_at + __popc(S & lanemask_lt());
+        a.idx_out[at] = idx[k];
+        a.sapos_out[at] = sap[k];
+        a.gd_out[at] = gd_run + __popc(SH & le) - 1;
+      }
     }
-  }
-  if (a.pairs && full) {
-    ulonglong2* pp = reinterpret_cast<ulonglong2*>(a.pairs + q0);
-#pragma unroll
-    for (int j = 0; j < RR_ITEMS / 2; ++j) pp[j] = make_ulonglong2(pr[2 * j], pr[2 * j + 1]);
+    if (H[k]) run_head = wbase + k * 32 + (31 - __clz(H[k])) + 1;
+    out_at += __popc(S);
+    gd_run += __popc(SH);
   }
   if (tile == a.tiles - 1 && tid == RR_THREADS - 1) {
-    a.totals[0] = s_carry[1] + uint32_t(tile_sum);
-    a.totals[1] = s_carry[2] + uint32_t(tile_sum >> 32);
+    a.totals[0] = s_carry[1] + tile_surv;
+    a.totals[1] = s_carry[2] + tile_shead;
   }
 }
 

@@ -98,85 +98,110 @@ __device__ __forceinline__ void copy_run(uint8_t* __restrict__ dst, const uint8_
   if (tid < len - done) dst[done + tid] = s_src[done + tid];
 }
 
+// Lane l of a warp holds the 16-byte pieces wbase/16 + 32 r + l (r = 0 .. 3) of the warp's 2 KB: every
+// load of a row is one coalesced 512-byte access (a first version gave each thread 64 consecutive
+// bytes: 20 sectors per load request in ncu), zero counts are scanned per row with one packed
+// warp scan, and two neighbouring lanes of a row make one rank word.
+constexpr int WV_ROWS = WV_BYTES / 16;             // 16-byte pieces per thread
+
 __global__ void __launch_bounds__(WV_THREADS) wavelet_pass_kernel(WaveletPass p) {
   __shared__ __align__(16) uint8_t s_bytes[WV_TILE + 16];
-  __shared__ uint32_t s_scan[WV_THREADS / 32];
+  __shared__ uint32_t s_wz[WV_THREADS / 32];
   __shared__ uint32_t s_tile, s_carry;
 
-  const unsigned tid = threadIdx.x;
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t base = tile * uint32_t(WV_TILE);
-  const uint32_t pos0 = base + tid * WV_BYTES;
-  const uint32_t nvalid = pos0 >= p.n ? 0u : min(uint32_t(WV_BYTES), p.n - pos0);
+  const uint32_t wbase = base + warp * (32 * WV_BYTES);
 
-  // input buffers are padded to a multiple of 64 bytes past n, so the vector loads are safe
-  uint32_t w[16];
-  if (nvalid) {
-    const uint4* src = reinterpret_cast<const uint4*>(p.in + pos0);
+  // input buffers are padded to a multiple of 64 bytes past n, so a piece that starts below n is readable
+  uint32_t w[WV_ROWS][4];
+  uint32_t ones[WV_ROWS], nvalid[WV_ROWS];
+  uint64_t packed = 0;                               // zero counts of the four pieces, 16 bits each
+#pragma unroll
+  for (int r = 0; r < WV_ROWS; ++r) {
+    const uint32_t pos = wbase + (r * 32 + lane) * 16;
+    nvalid[r] = pos >= p.n ? 0u : min(16u, p.n - pos);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (nvalid[r]) v = *reinterpret_cast<const uint4*>(p.in + pos);
+    w[r][0] = v.x; w[r][1] = v.y; w[r][2] = v.z; w[r][3] = v.w;
+    uint32_t o = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint4 v = src[q];
-      w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+      const uint32_t t = (w[r][q] >> p.bit) & 0x01010101u;
+      o |= ((t | (t >> 7) | (t >> 14) | (t >> 21)) & 15u) << (4 * q);
     }
-  } else {
-#pragma unroll
-    for (int q = 0; q < 16; ++q) w[q] = 0;
+    if (nvalid[r] < 16) o &= (1u << nvalid[r]) - 1u;
+    ones[r] = o;
+    packed |= uint64_t(nvalid[r] - __popc(o)) << (16 * r);
   }
-  // bit j of the 64 bytes, position order: 4 bits per 32-bit word
-  uint64_t ones = 0;
+  uint64_t inc = packed;                             // inclusive scan over the lanes, all four rows at once
 #pragma unroll
-  for (int q = 0; q < 16; ++q) {
-    const uint32_t t = (w[q] >> p.bit) & 0x01010101u;
-    const uint32_t nib = (t | (t >> 7) | (t >> 14) | (t >> 21)) & 15u;
-    ones |= uint64_t(nib) << (4 * q);
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= unsigned(d)) inc += o;
   }
-  if (nvalid < 64) ones &= (nvalid ? ((1ull << nvalid) - 1ull) : 0ull);
-  const uint32_t n1 = __popcll(ones), n0 = nvalid - n1;
-
-  uint32_t tile_zeros;
-  const uint32_t z_before_local = block_exclusive_scan<uint32_t, WV_THREADS>(n0, s_scan, tile_zeros);
+  const uint64_t rowtot = __shfl_sync(0xffffffffu, inc, 31);
+  const uint64_t excl = inc - packed;
+  uint32_t zrow[WV_ROWS];                            // zeros of the warp before this lane's piece of row r
+  uint32_t acc = 0;
+#pragma unroll
+  for (int r = 0; r < WV_ROWS; ++r) {
+    zrow[r] = acc + (uint32_t(excl >> (16 * r)) & 0xFFFFu);
+    acc += uint32_t(rowtot >> (16 * r)) & 0xFFFFu;
+  }
+  if (lane == 0) s_wz[warp] = acc;
+  __syncthreads();
+  uint32_t z_warp = 0, tile_zeros = 0;
+#pragma unroll
+  for (int k = 0; k < WV_THREADS / 32; ++k) {
+    const uint32_t z = s_wz[k];
+    if (unsigned(k) < warp) z_warp += z;
+    tile_zeros += z;
+  }
   if (tid < 32) {                        // warp-wide chained scan (a single thread made every tile wait, see profiles/)
     const uint32_t pre = lookback_warp_wide<4>(p.desc, tile, 0u, p.tag, tile_zeros, p.err);
     if (tid == 0) s_carry = pre;
   }
   __syncthreads();
-  const uint32_t z_before = s_carry + z_before_local;       // zeros in [0, pos0)
-  const uint32_t o_before = pos0 - z_before;                // ones  in [0, pos0)   (pos0 <= n here or unused)
+  const uint32_t carry = s_carry;
 
-  // (a) rank words: every thread owns two
-  {
-    const uint32_t word = pos0 / 32;
-    const uint32_t lo = uint32_t(ones), hi = uint32_t(ones >> 32);
-    const uint64_t r0 = (uint64_t(lo) << 32) | o_before;
-    const uint64_t r1 = (uint64_t(hi) << 32) | (o_before + __popc(lo));
-    // (a level's words start at an 8-byte boundary only: n/32 + 1 may be odd)
-    if (pos0 <= p.n) p.rank[word] = r0;
-    if (pos0 + 32 <= p.n) p.rank[word + 1] = r1;
+  // (a) rank words: two neighbouring lanes of a row make one 32-bit data word
+#pragma unroll
+  for (int r = 0; r < WV_ROWS; ++r) {
+    const uint32_t pos = wbase + (r * 32 + lane) * 16;
+    const uint32_t hi = __shfl_down_sync(0xffffffffu, ones[r], 1);
+    if (!(lane & 1u) && pos <= p.n) {
+      const uint32_t z_before = carry + z_warp + zrow[r];              // zeros in [0, pos)
+      p.rank[pos / 32] = (uint64_t(ones[r] | (hi << 16)) << 32) | (pos - z_before);
+    }
   }
   if (!p.out) return;
 
   // (b) stable partition through shared memory: zeros of the tile first, then ones
-  {
-    uint32_t zl = z_before_local;
-    uint32_t ol = tile_zeros + (tid * WV_BYTES - z_before_local);   // ones before, tile-local
-    // positions past n sit at the very end of the last tile and are never copied out
-    if (nvalid == WV_BYTES) {
 #pragma unroll
-      for (int k = 0; k < 64; ++k) {
-        const uint8_t b = uint8_t(w[k >> 2] >> (8 * (k & 3)));
-        const uint32_t one = uint32_t(ones >> k) & 1u;
+  for (int r = 0; r < WV_ROWS; ++r) {
+    const uint32_t local = warp * (32 * WV_BYTES) + (r * 32 + lane) * 16;   // tile-local position of the piece
+    uint32_t zl = z_warp + zrow[r];
+    uint32_t ol = tile_zeros + (local - zl);
+    // positions past n sit at the very end of the last tile and are never copied out
+    if (nvalid[r] == 16) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const uint8_t b = uint8_t(w[r][k >> 2] >> (8 * (k & 3)));
+        const uint32_t one = (ones[r] >> k) & 1u;
         s_bytes[one ? ol : zl] = b;
         ol += one;
         zl += one ^ 1u;
       }
     } else {
 #pragma unroll
-      for (int k = 0; k < 64; ++k) {
-        if (uint32_t(k) < nvalid) {
-          const uint8_t b = uint8_t(w[k >> 2] >> (8 * (k & 3)));
-          if ((ones >> k) & 1u) s_bytes[ol++] = b; else s_bytes[zl++] = b;
+      for (int k = 0; k < 16; ++k) {
+        if (uint32_t(k) < nvalid[r]) {
+          const uint8_t b = uint8_t(w[r][k >> 2] >> (8 * (k & 3)));
+          if ((ones[r] >> k) & 1u) s_bytes[ol++] = b; else s_bytes[zl++] = b;
         }
       }
     }
@@ -184,8 +209,8 @@ __global__ void __launch_bounds__(WV_THREADS) wavelet_pass_kernel(WaveletPass p)
   __syncthreads();
   const uint32_t tile_valid = base >= p.n ? 0u : min(uint32_t(WV_TILE), p.n - base);
   const uint32_t tile_ones = tile_valid - tile_zeros;
-  const uint32_t gz = s_carry;                              // zeros before the tile
-  const uint32_t go = p.zeros[p.bit] + (base - s_carry);    // ones region starts at Z_j
+  const uint32_t gz = carry;                                // zeros before the tile
+  const uint32_t go = p.zeros[p.bit] + (base - carry);      // ones region starts at Z_j
   copy_run(p.out + gz, s_bytes, tile_zeros, tid);
   copy_run(p.out + go, s_bytes + tile_zeros, tile_ones, tid);
 }

@@ -41,28 +41,25 @@ __device__ __forceinline__ uint64_t bswap64(uint64_t v) {
   return (uint64_t(__byte_perm(lo, 0, 0x0123)) << 32) | __byte_perm(hi, 0, 0x0123);
 }
 
+// Thread t of a CTA makes keys tile + 256 r + t (r = 0 .. 7): the 12 bytes a key and its index take are
+// written as coalesced rows (the first version wrote 64 bytes per thread: 32 sectors per store request).
+constexpr int PK_ROWS = 8;
+
 __global__ void __launch_bounds__(256) pack_keys_kernel(const uint8_t* __restrict__ T, uint32_t n,
                                                         uint64_t* __restrict__ keys,
                                                         uint32_t* __restrict__ idx) {
-  const uint32_t octets = (n + 7) / 8;
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= octets) return;
   const uint64_t* T64 = reinterpret_cast<const uint64_t*>(T);
-  uint64_t b0 = bswap64(T64[t]), b1 = bswap64(T64[t + 1]);
-  uint64_t k[8];
-  k[0] = b0;
+  const uint32_t tile = blockIdx.x * (256 * PK_ROWS);
 #pragma unroll
-  for (int j = 1; j < 8; ++j) k[j] = (b0 << (8 * j)) | (b1 >> (64 - 8 * j));
-  const uint32_t i0 = t * 8;
-  if (i0 + 8 <= n) {
-    ulonglong2* ko = reinterpret_cast<ulonglong2*>(keys + i0);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) ko[j] = make_ulonglong2(k[2 * j], k[2 * j + 1]);
-    uint4* io = reinterpret_cast<uint4*>(idx + i0);
-    io[0] = make_uint4(i0, i0 + 1, i0 + 2, i0 + 3);
-    io[1] = make_uint4(i0 + 4, i0 + 5, i0 + 6, i0 + 7);
-  } else {
-    for (int j = 0; j < 8 && i0 + j < n; ++j) { keys[i0 + j] = k[j]; idx[i0 + j] = i0 + j; }
+  for (int r = 0; r < PK_ROWS; ++r) {
+    const uint32_t i = tile + r * 256 + threadIdx.x;
+    if (i < n) {
+      // the text is cyclic for 64 bytes past n (pad_cyclic_kernel), so both words exist
+      const uint64_t a = bswap64(T64[i >> 3]), b = bswap64(T64[(i >> 3) + 1]);
+      const uint32_t sh = (i & 7u) * 8;
+      keys[i] = sh ? (a << sh) | (b >> (64 - sh)) : a;
+      idx[i] = i;
+    }
   }
 }
 
@@ -390,8 +387,7 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
 
   pad_cyclic_kernel<<<1, 64, 0, st>>>(T, n);
   {
-    uint32_t octets = (n + 7) / 8;
-    pack_keys_kernel<<<(octets + 255) / 256, 256, 0, st>>>(T, n, keyA, idxA);
+    pack_keys_kernel<<<(n + 256 * PK_ROWS - 1) / (256 * PK_ROWS), 256, 0, st>>>(T, n, keyA, idxA);
     S.gpu_launches += 2;
   }
   BCE_CUDA(c, cudaGetLastError());

@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
   __shared__ unsigned long long s_emitted[8];
   __shared__ uint32_t s_flags[2];
   __shared__ uint32_t s_lt[8], s_srt[8], s_cum[9];               // interleaved tile schedule (see locate)
+  constexpr int SCHED_CAP = 1024;                                // this CTA's first tiles of a round, located once
+  __shared__ uint32_t s_sched[SCHED_CAP];                        // (level << 28) | row in the level's chain
 
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   CseDeviceState* S = a.st;
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
 
     // ---- the tile being computed -------------------------------------------------------------
     uint32_t tile = blockIdx.x;
+    uint32_t seq = 0;                                       // tiles of this round taken by this CTA so far
     bool have = tile < total_tiles;
     int l = 0, hh = 0, nv = 0;
     uint32_t tj = 0;                                        // position of the tile in its level's chain
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
     // that still have a tile r, so the gridDim tiles that run at the same time are spread
     // over all 8 chains instead of being consecutive links of one.  Returns the level, half,
     // this thread's nodes and the tile's position tj in its level's chain.
-    auto locate = [&](uint32_t t, int& tl, int& th, int& tnv, uint32_t& to0, uint32_t& ttj) {
+    auto locate_row = [&](uint32_t t, int& tl, uint32_t& r_out) {
       int seg = 0;
 #pragma unroll
       for (int i = 1; i < 8; ++i)
@@ -148,6 +151,26 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
           if (pick == 0) { tl = k; found = true; } else --pick;
         }
       }
+      r_out = r;
+    };
+    // every warp used to repeat locate_row for every tile (8 % of the kernel's instructions): the CTA's
+    // tiles of the round are located once, cooperatively, and looked up afterwards
+    {
+      const uint32_t mine = blockIdx.x < total_tiles ? (total_tiles - blockIdx.x - 1) / gridDim.x + 1 : 0u;
+      const uint32_t fill = min(mine, uint32_t(SCHED_CAP));
+      for (uint32_t i = tid; i < fill; i += CS_THREADS) {
+        int tl;
+        uint32_t r;
+        locate_row(blockIdx.x + i * gridDim.x, tl, r);
+        s_sched[i] = (uint32_t(tl) << 28) | r;
+      }
+    }
+    __syncthreads();
+    // seq = how many tiles of this round the CTA has taken before tile t
+    auto locate = [&](uint32_t t, uint32_t seq, int& tl, int& th, int& tnv, uint32_t& to0, uint32_t& ttj) {
+      uint32_t r;
+      if (seq < uint32_t(SCHED_CAP)) { const uint32_t e = s_sched[seq]; tl = int(e >> 28); r = e & 0x0FFFFFFFu; }
+      else locate_row(t, tl, r);
       ttj = r;
       const uint32_t th0 = (s_cnt[tl][0] + TILE - 1) / TILE;
       th = r < th0 ? 0 : 1;
@@ -178,7 +201,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
 
     if (have) {
       uint32_t o0;
-      locate(tile, l, hh, nv, o0, tj);
+      locate(tile, 0u, l, hh, nv, o0, tj);
       load_nodes(l, hh, nv, o0);
       gather(l, (a.dbg & 2u) ? 0 : nv);
     }
@@ -260,7 +283,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
       uint32_t tj2 = 0;
       if (have_next) {
         uint32_t o02;
-        locate(next, l2, hh2, nv2, o02, tj2);
+        locate(next, ++seq, l2, hh2, nv2, o02, tj2);
         load_nodes(l2, hh2, nv2, o02);
       }
       // ---- resolve(i-1) --------------------------------------------------------------------------

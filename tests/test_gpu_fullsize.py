@@ -94,3 +94,21 @@ def test_scan_then_compress_with_config(frontend):
     assert arc == host.encode_archive(Cv, streams, T.size, off, cfg=cfg, threads=8)
     if oracle.have_ref():
         assert oracle.ref_decompress(arc) == T.tobytes()
+
+
+def test_two_gigabyte_input_near_the_size_limit(frontend):
+    """n = 2.1e9 (the format allows n <= 2^31 - 1): every 32-bit position, tile index and descriptor
+    offset is exercised close to its limit.  Checked by the device round trip
+    inverse(wavelet(BWT(T))) == T and the level loop's visit count 8(n - 1)."""
+    n = 2_100_000_000
+    T = np.frombuffer(synth.generate("enwik-shaped", n, 9), dtype=np.uint8)
+    L, off, _ = frontend.bwt(T)
+    assert (np.bincount(L, minlength=256) == np.bincount(T, minlength=256)).all()
+    ranks, _ = frontend.wavelet(L)
+    out = np.frombuffer(frontend.unbwt(ranks, off, n), dtype=np.uint8)
+    assert np.array_equal(out, T)
+    del ranks, L, out
+    frontend.stage_input(T)
+    frontend.front_resident()
+    st = frontend.stats()
+    assert st["cse_visits"] == 8 * (n - 1)

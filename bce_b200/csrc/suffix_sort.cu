@@ -80,6 +80,8 @@ struct RerankArgs {
   uint32_t* sa;
   uint32_t* rnk;
   uint64_t* pairs;          // when set: (idx << 32 | rank) per slot instead of the random rank scatter
+  uint32_t* part_cursor;    // when set: [256] write cursors; the pairs go out binned by idx >> part_shift
+  int part_shift;           //   (order inside a bin is irrelevant: every pair is a store to its own address)
   uint32_t* idx_out;        // compacted working set of the next round
   uint32_t* sapos_out;
   uint32_t* gd_out;         // dense group id of every survivor
@@ -102,12 +104,17 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
   __shared__ uint32_t s_whead[RR_WARPS], s_wsurv[RR_WARPS], s_wshead[RR_WARPS];
   __shared__ uint32_t s_tile;
   __shared__ uint32_t s_carry[3];
+  __shared__ uint32_t s_bcnt[256], s_bstart[256], s_gbase[256];   // binned pairs: per-bin count, tile-local start, global start
+  __shared__ uint32_t s_bscan[RR_WARPS];
+  __shared__ uint64_t s_stage[RR_TILE];
 
   const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+  s_bcnt[tid] = 0;
   __syncthreads();
   const uint32_t tile = s_tile;
   const uint32_t wbase = tile * RR_TILE + warp * RR_WCHUNK;      // < 2^32: m < 2^31
+  const bool binned = a.pairs && a.part_cursor;
 
   uint64_t key[RR_ROWS];
   uint32_t idx[RR_ROWS], sap[RR_ROWS];
@@ -118,6 +125,16 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
     key[k] = in ? a.key[q] : 0;
     idx[k] = in ? a.idx[q] : 0;
     sap[k] = in ? (a.sapos ? a.sapos[q] : q) : 0;
+  }
+  // binned pairs, step 1: every slot takes a place in its bin (any order), bins get their sizes
+  uint32_t bpos[RR_ROWS / 2];                       // two 16-bit places per register
+  if (binned) {
+#pragma unroll
+    for (int k = 0; k < RR_ROWS; ++k) {
+      const uint32_t q = wbase + k * 32 + lane;
+      const uint32_t at = q < a.m ? atomicAdd(&s_bcnt[(idx[k] >> a.part_shift) & 255u], 1u) : 0u;
+      bpos[k / 2] = (k & 1) ? (bpos[k / 2] | (at << 16)) : at;
+    }
   }
   // the keys just outside the warp's chunk (uniform loads)
   const uint64_t key_before = (wbase > 0 && wbase - 1 < a.m) ? a.key[wbase - 1] : 0;
@@ -160,6 +177,12 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
   }
   if (lane == 0) { s_whead[warp] = whead; s_wsurv[warp] = wsurv; s_wshead[warp] = wshead; }
   __syncthreads();
+  if (binned) {   // step 2: thread d owns bin d: room in the bin's global run, start inside the staging buffer
+    const uint32_t c = s_bcnt[tid];
+    uint32_t tot;
+    s_bstart[tid] = block_exclusive_scan<uint32_t, RR_THREADS>(c, s_bscan, tot);
+    s_gbase[tid] = c ? atomicAdd(&a.part_cursor[tid], c) : 0u;
+  }
   uint32_t head_before = 0, surv_before = 0, shead_before = 0, tile_head = 0, tile_surv = 0, tile_shead = 0;
 #pragma unroll
   for (int w = 0; w < RR_WARPS; ++w) {
@@ -196,7 +219,8 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
       const uint32_t rank = sap[k] - (q - (my_head - 1));
       // SA is final for a slot once its group is a single rotation; tied slots come back next round
       if (((L >> lane) & 1u) && !(a.dbg & 2u)) a.sa[sap[k]] = idx[k];
-      if (a.pairs) a.pairs[q] = (uint64_t(idx[k]) << 32) | rank;
+      if (binned) s_stage[s_bstart[(idx[k] >> a.part_shift) & 255u] + ((bpos[k / 2] >> ((k & 1) * 16)) & 0xFFFFu)] = (uint64_t(idx[k]) << 32) | rank;
+      else if (a.pairs) a.pairs[q] = (uint64_t(idx[k]) << 32) | rank;
       else if (!(a.dbg & 1u)) a.rnk[idx[k]] = rank;
       if (((S >> lane) & 1u) && !(a.dbg & 4u)) {
         const uint32_t at = out_at + __popc(S & lanemask_lt());
@@ -209,10 +233,26 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
     out_at += __popc(S);
     gd_run += __popc(SH);
   }
+  if (binned) {   // step 3: the staged pairs leave as one run per bin
+    __syncthreads();
+    const uint32_t tile_valid = min(uint32_t(RR_TILE), a.m - tile * RR_TILE);
+    for (uint32_t j = tid; j < tile_valid; j += RR_THREADS) {
+      const uint64_t pr = s_stage[j];
+      const uint32_t d = (uint32_t(pr >> 32) >> a.part_shift) & 255u;
+      a.pairs[s_gbase[d] + (j - s_bstart[d])] = pr;
+    }
+  }
   if (tile == a.tiles - 1 && tid == RR_THREADS - 1) {
     a.totals[0] = s_carry[1] + tile_surv;
     a.totals[1] = s_carry[2] + tile_shead;
   }
+}
+
+// bin starts of the binned pairs: exclusive scan of the bin sizes
+__global__ void __launch_bounds__(256) partition_cursor_kernel(const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor) {
+  __shared__ uint32_t s_scan[8];
+  uint32_t tot;
+  cursor[threadIdx.x] = block_exclusive_scan<uint32_t, 256>(hist[threadIdx.x], s_scan, tot);
 }
 
 // K3b: ranks from (idx, rank) pairs that were partitioned by the top bits of idx
@@ -366,6 +406,7 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
   uint32_t* d_totals = reinterpret_cast<uint32_t*>(small + kSmallRerankTotals);
   uint32_t* d_hist = reinterpret_cast<uint32_t*>(small + kSmallHist);
   uint32_t* d_phist = reinterpret_cast<uint32_t*>(small + kSmallPartHist);
+  uint32_t* d_pcursor = d_phist + 256;
   uint32_t* h_small = c->pinned_small.as<uint32_t>() + 8192;   // past the sort's host mirror
   BCE_CUDA(c, cudaMemsetAsync(d_err, 0, 64, st));
 
@@ -456,6 +497,25 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     // the rank array then stays in L2 while it is being filled.
     uint64_t* pair_buf = (ks == keyA) ? keyB : keyA;
     a.pairs = partitioned ? pair_buf : nullptr;
+    // the pairs leave the kernel already binned by the top bits of idx (BCE_GPU_PARTITION=radix: in slot
+    // order, binned afterwards by one keys-only radix pass)
+    const bool binned = partitioned && !getenv("BCE_GPU_PARTITION");
+    a.part_cursor = nullptr;
+    a.part_shift = pshift - 32;
+    if (binned) {
+      if (round == 0) {                  // every idx in [0, n) is present: the bin sizes are arithmetic
+        uint32_t* all_idx = h_small + 16;
+        const int sft = pshift - 32;
+        for (uint32_t d = 0; d < 256; ++d) {
+          const uint64_t lo = uint64_t(d) << sft, hi = uint64_t(d + 1) << sft;
+          all_idx[d] = uint32_t(lo >= n ? 0 : (hi < n ? hi : n) - lo);
+        }
+        BCE_CUDA(c, cudaMemcpyAsync(d_phist, all_idx, 256 * 4, cudaMemcpyHostToDevice, st));
+      }                                  // later rounds: counted by rekey_kernel over this round's working set
+      partition_cursor_kernel<<<1, 256, 0, st>>>(d_phist, d_pcursor);
+      S.gpu_launches++;
+      a.part_cursor = d_pcursor;
+    }
     a.idx_out = v_other; a.sapos_out = sap_next; a.gd_out = gd_next;
     a.totals = d_totals;
     a.tiles = (m + RR_TILE - 1) / RR_TILE;
@@ -475,7 +535,14 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
       BCE_TRY(lap(S.ms_rerank));      // synchronises
       BCE_TRACE("rerank round %d m=%u: %.3f ms (dbg=%u, partitioned=%d)", round, m, S.ms_rerank - before, a.dbg, int(partitioned));
       if (a.dbg) { set_error(c, "rerank timing experiment"); return BCE_GPU_E_INTERNAL; } }
-    if (partitioned) {
+    if (binned) {
+      scatter_ranks_kernel<<<(m + 255) / 256, 256, 0, st>>>(pair_buf, m, rnk);
+      S.gpu_launches++;
+      BCE_CUDA(c, cudaGetLastError());
+      const float before = S.ms_rerank;
+      BCE_TRY(lap(S.ms_rerank));
+      BCE_TRACE("rank scatter: %.3f ms", S.ms_rerank - before);
+    } else if (partitioned) {
       uint64_t* pk; uint32_t* pv; int pran = 0;
       RadixHistSource psrc;
       uint32_t all_idx[256];

@@ -70,6 +70,7 @@ constexpr size_t kSmallRerankTotals = kSmallRerankTicket + 64;  // 2 u32
 constexpr size_t kSmallWavelet = kSmallRerankTotals + 64;     // 256 u32 hist + 8 u32 zeros + 8 tickets
 constexpr size_t kSmallCse = kSmallWavelet + 2048;            // CseDeviceState
 constexpr size_t kSmallUnbwt = kSmallCse + 1024;              // inverse-BWT counters
+constexpr size_t kSmallRadixCursor = 52 * 1024;               // 256 u32      write cursors of a sort's first (unordered) pass
 constexpr size_t kSmallPartHist = 48 * 1024;                  // 256 u32      histogram of the rank-scatter partition digit
 constexpr size_t kSmallBytes = 64 * 1024;
 

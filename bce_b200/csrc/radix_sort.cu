@@ -186,6 +186,73 @@ unsigned peers;
   }
 }
 
+
+// ---- the first pass of a sort --------------------------------------------------------------
+// An LSD pass has to be stable only to keep what earlier passes established; the first pass has
+// nothing to keep (equal keys may come out in any order -- they are told apart, if at all, by later
+// rounds of the suffix sort).  So it needs neither the chained scan nor a stable ranking: a key
+// takes the next free place in its digit's bin of the tile (shared-memory atomic), the tile takes
+// room in the digit's global run with one atomicAdd per digit, and the staged keys leave as runs.
+template <int RS_ITEMS, int MIN_CTAS>
+__global__ void __launch_bounds__(256, MIN_CTAS) radix_unordered_kernel(RadixPass p, uint32_t* __restrict__ cursor) {
+  constexpr int RS_THREADS = 256;
+  constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+  extern __shared__ __align__(16) unsigned char ru_smem[];
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(ru_smem);                         // [RS_TILE]
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(ru_smem + size_t(RS_TILE) * 8);    // [RS_TILE]
+  __shared__ uint32_t s_cnt[256], s_start[256], s_goff[256];
+  __shared__ uint32_t s_scan[RS_THREADS / 32];
+
+  const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  s_cnt[tid] = 0;
+  __syncthreads();
+  const uint32_t tile_base = blockIdx.x * uint32_t(RS_TILE);
+  const uint32_t valid = min(uint32_t(RS_TILE), p.m - tile_base);
+  const uint32_t wbase = tile_base + warp * (32 * RS_ITEMS);
+  const bool has_vals = p.vin != nullptr;
+
+  uint64_t key[RS_ITEMS];
+  uint32_t val[RS_ITEMS];
+  uint32_t pos[RS_ITEMS / 2];                       // two 16-bit places per register
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const uint32_t idx = wbase + k * 32 + lane;
+    const bool in = idx < p.m;
+    key[k] = in ? p.kin[idx] : 0ull;
+    val[k] = (in && has_vals) ? p.vin[idx] : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    const bool in = wbase + k * 32 + lane < p.m;
+    const uint32_t at = in ? atomicAdd(&s_cnt[uint32_t(key[k] >> p.shift) & 255u], 1u) : 0u;
+    pos[k / 2] = (k & 1) ? (pos[k / 2] | (at << 16)) : at;
+  }
+  __syncthreads();
+  {
+    const uint32_t c = s_cnt[tid];
+    uint32_t tot;
+    const uint32_t st = block_exclusive_scan<uint32_t, RS_THREADS>(c, s_scan, tot);
+    s_start[tid] = st;
+    s_goff[tid] = p.base[tid] + (c ? atomicAdd(&cursor[tid], c) : 0u) - st;    // global index = s_goff[digit] + staged index
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; ++k) {
+    if (wbase + k * 32 + lane < p.m) {
+      const uint32_t at = s_start[uint32_t(key[k] >> p.shift) & 255u] + ((pos[k / 2] >> ((k & 1) * 16)) & 0xFFFFu);
+      s_keys[at] = key[k];
+      s_vals[at] = val[k];
+    }
+  }
+  __syncthreads();
+  for (uint32_t j = tid; j < valid; j += RS_THREADS) {
+    const uint64_t k64 = s_keys[j];
+    const uint32_t g = s_goff[uint32_t(k64 >> p.shift) & 255u] + j;
+    p.kout[g] = k64;
+    if (has_vals) p.vout[g] = s_vals[j];
+  }
+}
+
 }  // namespace bce
 
 #include "radix_chunked.cuh"
@@ -317,6 +384,7 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
     d_chist = c->radix_tmp.as<uint32_t>();
     d_offs = d_chist + size_t(chunks) * 256;
   }
+  const bool unordered_first = !getenv("BCE_GPU_RADIX_STABLE_FIRST");
   const double ballot_above = double(env_size_d("BCE_GPU_RADIX_BALLOT_ABOVE", 24.0));
   int ran = 0;
   for (int p = 0; p < npass; ++p) {
@@ -340,6 +408,17 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
       radix_chunk_scan_kernel<<<1, 256, 0, c->stream>>>(d_chist, chunks, d_offs);
       radix_downsweep_kernel<<<chunks, RD_THREADS, 0, c->stream>>>(dn);
       c->stats.gpu_launches += 2;
+    } else if (ran == 0 && unordered_first) {
+      uint32_t* d_cursor = reinterpret_cast<uint32_t*>(small + kSmallRadixCursor);
+      BCE_CUDA(c, cudaMemsetAsync(d_cursor, 0, 256 * 4, c->stream));
+      constexpr int UI = 24;
+      const size_t usmem = size_t(256) * UI * 12;
+      static bool uattr = false;
+      if (!uattr) {
+        BCE_CUDA(c, cudaFuncSetAttribute(radix_unordered_kernel<UI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(usmem)));
+        uattr = true;
+      }
+      radix_unordered_kernel<UI, 2><<<(m + 256 * UI - 1) / (256 * UI), 256, usmem, c->stream>>>(a, d_cursor);
     } else {
       // expected number of different digits among 32 keys drawn from this pass's histogram
       double distinct = 0;

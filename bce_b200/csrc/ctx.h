@@ -80,6 +80,8 @@ constexpr size_t kSmallBytes = 64 * 1024;
 // Where the digit histograms of a sort come from (default: one extra read of the keys).
 struct RadixHistSource {
   const uint8_t* window_text = nullptr;   // keys are the 8-byte cyclic windows of this text: its byte histogram serves every pass
+  bool keys_from_text = false;            // ... and keyA / valA are NOT filled: the first pass makes keys and indices from the
+                                          // text (if no pass runs at all -- one repeated byte -- the caller has to pack them)
   const uint32_t* dev_hist = nullptr;     // [npass][256] already counted on the device (e.g. by the kernel that wrote the keys);
                                           // may be Ctx::small + kSmallHist itself
   const uint32_t* host_hist = nullptr;    // [npass][256] known on the host

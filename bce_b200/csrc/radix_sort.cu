@@ -193,8 +193,16 @@ unsigned peers;
 // rounds of the suffix sort).  So it needs neither the chained scan nor a stable ranking: a key
 // takes the next free place in its digit's bin of the tile (shared-memory atomic), the tile takes
 // room in the digit's global run with one atomicAdd per digit, and the staged keys leave as runs.
-template <int RS_ITEMS, int MIN_CTAS>
-__global__ void __launch_bounds__(256, MIN_CTAS) radix_unordered_kernel(RadixPass p, uint32_t* __restrict__ cursor) {
+// FROM_TEXT: the keys are the 8-byte cyclic windows of `text` (big-endian) and the values their start
+// indices; they are made here instead of being read (no pack kernel, 1 byte read per key instead of 12).
+__device__ __forceinline__ uint64_t radix_bswap64(uint64_t v) {
+  const uint32_t lo = uint32_t(v), hi = uint32_t(v >> 32);
+  return (uint64_t(__byte_perm(lo, 0, 0x0123)) << 32) | __byte_perm(hi, 0, 0x0123);
+}
+
+template <int RS_ITEMS, int MIN_CTAS, bool FROM_TEXT>
+__global__ void __launch_bounds__(256, MIN_CTAS) radix_unordered_kernel(RadixPass p, uint32_t* __restrict__ cursor,
+                                                                        const uint8_t* __restrict__ text) {
   constexpr int RS_THREADS = 256;
   constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
   extern __shared__ __align__(16) unsigned char ru_smem[];
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(256, MIN_CTAS) radix_unordered_kernel(RadixPas
   const uint32_t tile_base = blockIdx.x * uint32_t(RS_TILE);
   const uint32_t valid = min(uint32_t(RS_TILE), p.m - tile_base);
   const uint32_t wbase = tile_base + warp * (32 * RS_ITEMS);
-  const bool has_vals = p.vin != nullptr;
+  const bool has_vals = FROM_TEXT || p.vin != nullptr;
 
   uint64_t key[RS_ITEMS];
   uint32_t val[RS_ITEMS];
@@ -218,8 +226,17 @@ __global__ void __launch_bounds__(256, MIN_CTAS) radix_unordered_kernel(RadixPas
   for (int k = 0; k < RS_ITEMS; ++k) {
     const uint32_t idx = wbase + k * 32 + lane;
     const bool in = idx < p.m;
-    key[k] = in ? p.kin[idx] : 0ull;
-    val[k] = (in && has_vals) ? p.vin[idx] : 0u;
+    if (FROM_TEXT) {
+      // the text is cyclic for 64 bytes past its end, so both words exist (see pad_cyclic_kernel)
+      const uint64_t* T64 = reinterpret_cast<const uint64_t*>(text);
+      const uint64_t a = in ? radix_bswap64(T64[idx >> 3]) : 0ull, b = in ? radix_bswap64(T64[(idx >> 3) + 1]) : 0ull;
+      const uint32_t sh = (idx & 7u) * 8;
+      key[k] = sh ? (a << sh) | (b >> (64 - sh)) : a;
+      val[k] = idx;
+    } else {
+      key[k] = in ? p.kin[idx] : 0ull;
+      val[k] = (in && has_vals) ? p.vin[idx] : 0u;
+    }
   }
 #pragma unroll
   for (int k = 0; k < RS_ITEMS; ++k) {
@@ -415,10 +432,13 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
       const size_t usmem = size_t(256) * UI * 12;
       static bool uattr = false;
       if (!uattr) {
-        BCE_CUDA(c, cudaFuncSetAttribute(radix_unordered_kernel<UI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(usmem)));
+        BCE_CUDA(c, cudaFuncSetAttribute(radix_unordered_kernel<UI, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(usmem)));
+        BCE_CUDA(c, cudaFuncSetAttribute(radix_unordered_kernel<UI, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(usmem)));
         uattr = true;
       }
-      radix_unordered_kernel<UI, 2><<<(m + 256 * UI - 1) / (256 * UI), 256, usmem, c->stream>>>(a, d_cursor);
+      const uint32_t ugrid = (m + 256 * UI - 1) / (256 * UI);
+      if (src && src->keys_from_text) radix_unordered_kernel<UI, 2, true><<<ugrid, 256, usmem, c->stream>>>(a, d_cursor, window_text);
+      else radix_unordered_kernel<UI, 2, false><<<ugrid, 256, usmem, c->stream>>>(a, d_cursor, nullptr);
     } else {
       // expected number of different digits among 32 keys drawn from this pass's histogram
       double distinct = 0;

@@ -427,9 +427,13 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
   BCE_CUDA(c, cudaEventRecord(e0, st));
 
   pad_cyclic_kernel<<<1, 64, 0, st>>>(T, n);
-  {
+  S.gpu_launches++;
+  // the first radix pass of round 0 makes keys and indices from the text itself (BCE_GPU_PACK=1: a
+  // separate pack kernel writes them first)
+  const bool fused_pack = !getenv("BCE_GPU_PACK") && !getenv("BCE_GPU_RADIX_STABLE_FIRST") && !getenv("BCE_GPU_RADIX");
+  if (!fused_pack) {
     pack_keys_kernel<<<(n + 256 * PK_ROWS - 1) / (256 * PK_ROWS), 256, 0, st>>>(T, n, keyA, idxA);
-    S.gpu_launches += 2;
+    S.gpu_launches++;
   }
   BCE_CUDA(c, cudaGetLastError());
   BCE_TRY(lap(S.ms_pack));
@@ -478,8 +482,12 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     BCE_TRACE("sort round %d m=%u h=%llu tiebreak=%d passes<=%d", round, m, (unsigned long long)h, int(tiebreak), np);
     uint64_t* ks; uint32_t* vs; int ran = 0;
     RadixHistSource hsrc;
-    if (round == 0) hsrc.window_text = T; else hsrc.dev_hist = d_hist;
+    if (round == 0) { hsrc.window_text = T; hsrc.keys_from_text = fused_pack; } else hsrc.dev_hist = d_hist;
     BCE_TRY(radix_sort_pairs(c, kcur, kalt, vcur, valt, m, shifts, np, &ks, &vs, &ran, &hsrc));
+    if (round == 0 && fused_pack && ran == 0) {      // every window is the same byte repeated: no pass ran, nothing made the keys
+      pack_keys_kernel<<<(n + 256 * PK_ROWS - 1) / (256 * PK_ROWS), 256, 0, st>>>(T, n, ks, vs);
+      S.gpu_launches++;
+    }
     BCE_TRY(lap(S.ms_radix));
     S.sort_m[round] = m;
     S.sort_passes[round] = uint32_t(ran);

@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "ctx.h"
+#include "local_sort.cuh"
 
 namespace bce {
 
@@ -385,7 +386,11 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
 
   // scratch: two key buffers, two index buffers, SA, rank, and the positional side arrays
   const size_t N = n;
-  size_t need = 2 * Carver::need(N, 8) + 8 * Carver::need(N, 4) + 4096;
+  // fall-back list of the tile-local sort (local_sort.cuh): at most a quarter of the working set
+  const size_t FB = N / 4 + 1;
+  const size_t LT = N / LS_TILE + 2;
+  size_t need = 2 * Carver::need(N, 8) + 8 * Carver::need(N, 4) + 2 * Carver::need(FB, 8) + 3 * Carver::need(FB, 4) +
+                4 * Carver::need(LT, 4) + 4096;
   BCE_TRY(c->scratch.ensure(c, need));
   Carver cv(c->scratch.p, c->scratch.cap);
   uint64_t* keyA = cv.take<uint64_t>(N);
@@ -398,6 +403,15 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
   uint32_t* saposB = cv.take<uint32_t>(N);
   uint32_t* gdA = cv.take<uint32_t>(N);
   uint32_t* gdB = cv.take<uint32_t>(N);
+  uint64_t* fbkA = cv.take<uint64_t>(FB);
+  uint64_t* fbkB = cv.take<uint64_t>(FB);
+  uint32_t* fbvA = cv.take<uint32_t>(FB);
+  uint32_t* fbvB = cv.take<uint32_t>(FB);
+  uint32_t* fb_slot = cv.take<uint32_t>(FB);
+  uint32_t* lt_pre = cv.take<uint32_t>(LT);
+  uint32_t* lt_suf = cv.take<uint32_t>(LT);
+  uint32_t* lt_cnt = cv.take<uint32_t>(LT);
+  uint32_t* lt_off = cv.take<uint32_t>(LT);
   if (!cv.ok()) { set_error(c, "suffix sort: scratch carve failed"); return BCE_GPU_E_NOMEM; }
 
   char* small = c->small.as<char>();
@@ -430,6 +444,7 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
   S.gpu_launches++;
   // the first radix pass of round 0 makes keys and indices from the text itself (BCE_GPU_PACK=1: a
   // separate pack kernel writes them first)
+  const bool use_local = !getenv("BCE_GPU_NO_LOCAL_SORT");
   const bool fused_pack = !getenv("BCE_GPU_PACK") && !getenv("BCE_GPU_RADIX_STABLE_FIRST") && !getenv("BCE_GPU_RADIX");
   if (!fused_pack) {
     pack_keys_kernel<<<(n + 256 * PK_ROWS - 1) / (256 * PK_ROWS), 256, 0, st>>>(T, n, keyA, idxA);
@@ -481,9 +496,44 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     }
     BCE_TRACE("sort round %d m=%u h=%llu tiebreak=%d passes<=%d", round, m, (unsigned long long)h, int(tiebreak), np);
     uint64_t* ks; uint32_t* vs; int ran = 0;
+    // Rounds >= 1: the groups are short, so tiles are sorted where they are and only the groups that
+    // cross a tile boundary go through the radix sort (local_sort.cuh)
+    bool local_done = false;
+    if (round >= 1 && use_local && m >= (1u << 20)) {
+      const uint32_t ltiles = (m + LS_TILE - 1) / LS_TILE;
+      ls_classify_kernel<<<(ltiles + 255) / 256, 256, 0, st>>>(kcur, m, ltiles, lt_pre, lt_suf, lt_cnt);
+      ls_scan_kernel<<<1, 1024, 0, st>>>(lt_cnt, ltiles, lt_off, d_totals + 3);
+      S.gpu_launches += 2;
+      BCE_CUDA(c, cudaGetLastError());
+      BCE_CUDA(c, cudaMemcpyAsync(h_small + 4, d_totals + 3, 4, cudaMemcpyDeviceToHost, st));
+      BCE_CUDA(c, cudaStreamSynchronize(st));
+      const uint32_t m_fb = h_small[4];
+      BCE_TRACE("local sort round %d: %u of %u slots in groups that cross a tile boundary", round, m_fb, m);
+      if (m_fb <= FB - 1 && m_fb <= m / 4) {
+        LocalSortArgs la;
+        la.kin = kcur; la.vin = vcur; la.kout = kalt; la.vout = valt; la.m = m;
+        la.pre = lt_pre; la.suf = lt_suf; la.off = lt_off;
+        la.fb_key = fbkA; la.fb_idx = fbvA; la.fb_slot = fb_slot;
+        ls_sort_kernel<<<ltiles, LS_THREADS, 0, st>>>(la);
+        S.gpu_launches++;
+        BCE_CUDA(c, cudaGetLastError());
+        if (m_fb) {
+          uint64_t* sk; uint32_t* sv; int fran = 0;
+          BCE_TRY(radix_sort_pairs(c, fbkA, fbkB, fbvA, fbvB, m_fb, shifts, np, &sk, &sv, &fran, nullptr));
+          ls_place_kernel<<<(m_fb + 255) / 256, 256, 0, st>>>(sk, sv, fb_slot, m_fb, kalt, valt);
+          S.gpu_launches++;
+          BCE_CUDA(c, cudaGetLastError());
+        }
+        ks = kalt; vs = valt;
+        ran = np;                        // reported as the passes an LSD sort of these keys would take
+        S.sort_local_elems += m;
+        S.sort_fallback_elems += m_fb;
+        local_done = true;
+      }
+    }
     RadixHistSource hsrc;
     if (round == 0) { hsrc.window_text = T; hsrc.keys_from_text = fused_pack; } else hsrc.dev_hist = d_hist;
-    BCE_TRY(radix_sort_pairs(c, kcur, kalt, vcur, valt, m, shifts, np, &ks, &vs, &ran, &hsrc));
+    if (!local_done) BCE_TRY(radix_sort_pairs(c, kcur, kalt, vcur, valt, m, shifts, np, &ks, &vs, &ran, &hsrc));
     if (round == 0 && fused_pack && ran == 0) {      // every window is the same byte repeated: no pass ran, nothing made the keys
       pack_keys_kernel<<<(n + 256 * PK_ROWS - 1) / (256 * PK_ROWS), 256, 0, st>>>(T, n, ks, vs);
       S.gpu_launches++;

@@ -65,7 +65,7 @@ class Stats(C.Structure):
         ("ms_unbwt_bytes", C.c_float), ("ms_unbwt_chase", C.c_float),
         ("ms_bwt_total", C.c_float), ("ms_cse_total", C.c_float), ("ms_total", C.c_float),
         ("ms_cse_narrow", C.c_float), ("cse_rounds_narrow", C.c_uint32), ("ms_radix_kernel", C.c_float),
-        ("cse_words", C.c_uint64),
+        ("cse_words", C.c_uint64), ("sort_local_elems", C.c_uint64), ("sort_fallback_elems", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

@@ -80,6 +80,9 @@ typedef struct bce_gpu_stats {
   uint32_t cse_rounds_narrow;    /* rounds run by it */
   float ms_radix_kernel;         /* sum over launches of radix_onesweep_kernel alone (event pairs) */
   uint64_t cse_words;            /* 32-bit words emitted (5 per count raw, 1-2 packed) */
+  uint64_t sort_local_elems;     /* elements of rounds >= 1 ordered by the tile-local sort instead of radix passes
+                                    (sort_passes[r] then holds the passes an LSD sort of those keys would take) */
+  uint64_t sort_fallback_elems;  /* ... of which went through the radix sort after all (groups crossing tiles) */
 } bce_gpu_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------- */

@@ -26,13 +26,13 @@ constexpr int LS_ITEMS = 16;
 constexpr int LS_TILE = LS_THREADS * LS_ITEMS;      // 4096
 
 // counts of non-local slots at the front (pre) and back (suf) of every tile
-__global__ void __launch_bounds__(256) ls_classify_kernel(const uint64_t* __restrict__ key, uint32_t m, uint32_t tiles,
+__global__ void __launch_bounds__(256) ls_classify_kernel(const uint32_t* __restrict__ gdv, uint32_t m, uint32_t tiles,
                                                           uint32_t* __restrict__ pre, uint32_t* __restrict__ suf,
                                                           uint32_t* __restrict__ cnt) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= tiles) return;
   const uint32_t start = t * uint32_t(LS_TILE), end = min(m, start + uint32_t(LS_TILE));
-  auto gd = [&](uint32_t q) { return uint32_t(key[q] >> 32); };
+  auto gd = [&](uint32_t q) { return gdv[q]; };
   uint32_t p = 0, s = 0;
   if (start > 0 && gd(start - 1) == gd(start)) {      // first group continues from the previous tile
     const uint32_t g = gd(start);
@@ -74,8 +74,11 @@ __global__ void __launch_bounds__(1024) ls_scan_kernel(const uint32_t* __restric
 }
 
 struct LocalSortArgs {
-  const uint64_t* kin;
-  const uint32_t* vin;
+  const uint32_t* vin;      // rotation start of every slot
+  const uint32_t* gd;       // dense group id of every slot (ascending)
+  const uint32_t* rnk;      // rank array: second = rnk[(idx + h) mod n], or idx itself in the tie-break round
+  uint32_t n, h;
+  int tiebreak;
   uint64_t* kout;
   uint32_t* vout;
   uint32_t m;
@@ -105,17 +108,26 @@ __global__ void __launch_bounds__(LS_THREADS) ls_sort_kernel(LocalSortArgs a) {
   const uint32_t tile = blockIdx.x;
   const uint32_t start = tile * uint32_t(LS_TILE);
   const uint32_t valid = min(uint32_t(LS_TILE), a.m - start);
-  const uint32_t gd0 = uint32_t(a.kin[start] >> 32);
+  const uint32_t gd0 = a.gd[start];
 
   // coalesced load into shared memory; the non-local slots go to the fall-back list on the way
   {
     const uint32_t p = a.pre[tile], sfx = a.suf[tile], o = a.off[tile];
     for (uint32_t j = tid; j < uint32_t(LS_TILE); j += LS_THREADS) {
       const bool in = j < valid;
-      const uint64_t k = in ? a.kin[start + j] : 0ull;
       const uint32_t v = in ? a.vin[start + j] : 0u;
+      const uint32_t g = in ? a.gd[start + j] : 0u;
+      // the key of the doubling step is made here (K4's gather): 16 independent gathers per thread in flight,
+      // and they overlap with the sorting networks of the other tiles on the SM
+      uint32_t second = v;
+      if (in && !a.tiebreak) {
+        uint64_t jj = uint64_t(v) + a.h;
+        if (jj >= a.n) jj -= a.n;
+        second = a.rnk[jj];
+      }
+      const uint64_t k = (uint64_t(g) << 32) | second;
       // padding sorts to the end of the tile
-      s_key[j] = in ? (uint64_t(uint32_t(k >> 32) - gd0) << 44) | (uint64_t(uint32_t(k)) << 12) | j : ~0ull;
+      s_key[j] = in ? (uint64_t(g - gd0) << 44) | (uint64_t(second) << 12) | j : ~0ull;
       s_val[j] = v;
       if (in) {
         uint32_t f = 0xFFFFFFFFu;
@@ -190,6 +202,23 @@ __global__ void __launch_bounds__(LS_THREADS) ls_sort_kernel(LocalSortArgs a) {
     a.kout[start + j] = (uint64_t(gd0 + uint32_t(w >> 44)) << 32) | uint32_t(w >> 12);
     a.vout[start + j] = s_val[uint32_t(w) & 4095u];
   }
+}
+
+// histogram of the rank-scatter partition digit (idx >> shift) over the working set (K4 counts it on the
+// radix path; here nothing else reads idx in a persistent shape)
+__global__ void __launch_bounds__(256) ls_idx_hist_kernel(const uint32_t* __restrict__ idx, uint32_t m, int shift,
+                                                          uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[8][256];
+  const unsigned tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 8 * 256; i += 256) (&h[0][0])[i] = 0;
+  __syncthreads();
+  for (uint64_t q = uint64_t(blockIdx.x) * 256 + tid; q < m; q += uint64_t(gridDim.x) * 256)
+    atomicAdd(&h[warp][(idx[q] >> shift) & 255u], 1u);
+  __syncthreads();
+  uint32_t v = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) v += h[w][tid];
+  if (v) atomicAdd(&hist[tid], v);
 }
 
 __global__ void __launch_bounds__(256) ls_place_kernel(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ sv,

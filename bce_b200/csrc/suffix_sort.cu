@@ -470,6 +470,8 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     // (see the re-rank step below); decided here because the key rebuild counts that digit too.
     const bool partitioned = !getenv("BCE_GPU_NO_PARTITION") && m >= (8u << 20) && size_t(n) * 4 > (size_t(64) << 20);
     const int pshift = 32 + std::max(0, nbits - 8);
+    bool local_plan = false;               // this round's sort is done tile by tile (local_sort.cuh)
+    uint32_t m_fb = 0;                     // ... except for this many slots, which go through the radix sort
     if (round == 0) {
       for (int s = 0; s < 64; s += 8) shifts[np++] = s;
     } else {
@@ -477,59 +479,74 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
       for (int s = 0; s < nbits; s += 8) shifts[np++] = s;
       int gbits = bits_for(groups);
       for (int s = 0; s < gbits && np < 8; s += 8) shifts[np++] = 32 + s;
-      // working-set slot -> key of the next doubling step, digit histograms counted on the way
-      RekeyHist rh;
-      for (int i = 0; i < kRadixMaxPasses; ++i) rh.sh.s[i] = i < np ? shifts[i] : 0;
-      rh.npass = np;
-      rh.hist = d_hist;
-      rh.phist = partitioned ? d_phist : nullptr;
-      rh.pshift = pshift - 32;
-      BCE_CUDA(c, cudaMemsetAsync(d_hist, 0, kRadixMaxPasses * 256 * 4, st));
-      BCE_CUDA(c, cudaMemsetAsync(d_phist, 0, 256 * 4, st));
-      const uint32_t chunk = RK_THREADS * RK_ITEMS;
-      const uint32_t want = (m + chunk - 1) / chunk, most = uint32_t(c->sm_count) * 8;
-      rekey_kernel<<<want < most ? want : most, RK_THREADS, 0, st>>>(vcur, gd_next == gdA ? gdB : gdA, rnk, m, n,
-                                                                     uint32_t(tiebreak ? 0 : h), tiebreak ? 1 : 0, kcur, rh);
-      S.gpu_launches++;
-      BCE_CUDA(c, cudaGetLastError());
-      BCE_TRY(lap(S.ms_rekey));
+      // Rounds >= 1: the groups are short, so tiles are sorted where they are (keys made on the way) and
+      // only the groups that cross a tile boundary go through the radix sort (local_sort.cuh)
+      uint32_t* gd_cur = gd_next == gdA ? gdB : gdA;
+      if (use_local && m >= (1u << 20)) {
+        const uint32_t ltiles = (m + LS_TILE - 1) / LS_TILE;
+        ls_classify_kernel<<<(ltiles + 255) / 256, 256, 0, st>>>(gd_cur, m, ltiles, lt_pre, lt_suf, lt_cnt);
+        ls_scan_kernel<<<1, 1024, 0, st>>>(lt_cnt, ltiles, lt_off, d_totals + 3);
+        S.gpu_launches += 2;
+        BCE_CUDA(c, cudaGetLastError());
+        BCE_CUDA(c, cudaMemcpyAsync(h_small + 4, d_totals + 3, 4, cudaMemcpyDeviceToHost, st));
+        BCE_CUDA(c, cudaStreamSynchronize(st));
+        m_fb = h_small[4];
+        BCE_TRACE("local sort round %d: %u of %u slots in groups that cross a tile boundary", round, m_fb, m);
+        local_plan = m_fb <= FB - 1 && m_fb <= m / 4;
+      }
+      if (local_plan) {
+        if (partitioned) {
+          BCE_CUDA(c, cudaMemsetAsync(d_phist, 0, 256 * 4, st));
+          const uint32_t want = (m + 255) / 256, most = uint32_t(c->sm_count) * 8;
+          ls_idx_hist_kernel<<<want < most ? want : most, 256, 0, st>>>(vcur, m, pshift - 32, d_phist);
+          S.gpu_launches++;
+        }
+        BCE_TRY(lap(S.ms_rekey));
+      } else {
+        // working-set slot -> key of the next doubling step, digit histograms counted on the way
+        RekeyHist rh;
+        for (int i = 0; i < kRadixMaxPasses; ++i) rh.sh.s[i] = i < np ? shifts[i] : 0;
+        rh.npass = np;
+        rh.hist = d_hist;
+        rh.phist = partitioned ? d_phist : nullptr;
+        rh.pshift = pshift - 32;
+        BCE_CUDA(c, cudaMemsetAsync(d_hist, 0, kRadixMaxPasses * 256 * 4, st));
+        BCE_CUDA(c, cudaMemsetAsync(d_phist, 0, 256 * 4, st));
+        const uint32_t chunk = RK_THREADS * RK_ITEMS;
+        const uint32_t want = (m + chunk - 1) / chunk, most = uint32_t(c->sm_count) * 8;
+        rekey_kernel<<<want < most ? want : most, RK_THREADS, 0, st>>>(vcur, gd_next == gdA ? gdB : gdA, rnk, m, n,
+                                                                       uint32_t(tiebreak ? 0 : h), tiebreak ? 1 : 0, kcur, rh);
+        S.gpu_launches++;
+        BCE_CUDA(c, cudaGetLastError());
+        BCE_TRY(lap(S.ms_rekey));
+      }
     }
     BCE_TRACE("sort round %d m=%u h=%llu tiebreak=%d passes<=%d", round, m, (unsigned long long)h, int(tiebreak), np);
     uint64_t* ks; uint32_t* vs; int ran = 0;
-    // Rounds >= 1: the groups are short, so tiles are sorted where they are and only the groups that
-    // cross a tile boundary go through the radix sort (local_sort.cuh)
     bool local_done = false;
-    if (round >= 1 && use_local && m >= (1u << 20)) {
+    if (local_plan) {
       const uint32_t ltiles = (m + LS_TILE - 1) / LS_TILE;
-      ls_classify_kernel<<<(ltiles + 255) / 256, 256, 0, st>>>(kcur, m, ltiles, lt_pre, lt_suf, lt_cnt);
-      ls_scan_kernel<<<1, 1024, 0, st>>>(lt_cnt, ltiles, lt_off, d_totals + 3);
-      S.gpu_launches += 2;
+      LocalSortArgs la;
+      la.vin = vcur; la.gd = gd_next == gdA ? gdB : gdA; la.rnk = rnk;
+      la.n = n; la.h = uint32_t(tiebreak ? 0 : h); la.tiebreak = tiebreak ? 1 : 0;
+      la.kout = kalt; la.vout = valt; la.m = m;
+      la.pre = lt_pre; la.suf = lt_suf; la.off = lt_off;
+      la.fb_key = fbkA; la.fb_idx = fbvA; la.fb_slot = fb_slot;
+      ls_sort_kernel<<<ltiles, LS_THREADS, 0, st>>>(la);
+      S.gpu_launches++;
       BCE_CUDA(c, cudaGetLastError());
-      BCE_CUDA(c, cudaMemcpyAsync(h_small + 4, d_totals + 3, 4, cudaMemcpyDeviceToHost, st));
-      BCE_CUDA(c, cudaStreamSynchronize(st));
-      const uint32_t m_fb = h_small[4];
-      BCE_TRACE("local sort round %d: %u of %u slots in groups that cross a tile boundary", round, m_fb, m);
-      if (m_fb <= FB - 1 && m_fb <= m / 4) {
-        LocalSortArgs la;
-        la.kin = kcur; la.vin = vcur; la.kout = kalt; la.vout = valt; la.m = m;
-        la.pre = lt_pre; la.suf = lt_suf; la.off = lt_off;
-        la.fb_key = fbkA; la.fb_idx = fbvA; la.fb_slot = fb_slot;
-        ls_sort_kernel<<<ltiles, LS_THREADS, 0, st>>>(la);
+      if (m_fb) {
+        uint64_t* sk; uint32_t* sv; int fran = 0;
+        BCE_TRY(radix_sort_pairs(c, fbkA, fbkB, fbvA, fbvB, m_fb, shifts, np, &sk, &sv, &fran, nullptr));
+        ls_place_kernel<<<(m_fb + 255) / 256, 256, 0, st>>>(sk, sv, fb_slot, m_fb, kalt, valt);
         S.gpu_launches++;
         BCE_CUDA(c, cudaGetLastError());
-        if (m_fb) {
-          uint64_t* sk; uint32_t* sv; int fran = 0;
-          BCE_TRY(radix_sort_pairs(c, fbkA, fbkB, fbvA, fbvB, m_fb, shifts, np, &sk, &sv, &fran, nullptr));
-          ls_place_kernel<<<(m_fb + 255) / 256, 256, 0, st>>>(sk, sv, fb_slot, m_fb, kalt, valt);
-          S.gpu_launches++;
-          BCE_CUDA(c, cudaGetLastError());
-        }
-        ks = kalt; vs = valt;
-        ran = np;                        // reported as the passes an LSD sort of these keys would take
-        S.sort_local_elems += m;
-        S.sort_fallback_elems += m_fb;
-        local_done = true;
       }
+      ks = kalt; vs = valt;
+      ran = np;                          // reported as the passes an LSD sort of these keys would take
+      S.sort_local_elems += m;
+      S.sort_fallback_elems += m_fb;
+      local_done = true;
     }
     RadixHistSource hsrc;
     if (round == 0) { hsrc.window_text = T; hsrc.keys_from_text = fused_pack; } else hsrc.dev_hist = d_hist;

@@ -558,6 +558,7 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     BCE_TRY(lap(S.ms_radix));
     S.sort_m[round] = m;
     S.sort_passes[round] = uint32_t(ran);
+    S.sort_radix_passes[round] = local_done ? 0u : uint32_t(ran);
     S.sort_rounds = uint32_t(round + 1);
 
     // re-rank: writes SA and rank for every slot, compacts the still-tied slots

@@ -66,13 +66,14 @@ class Stats(C.Structure):
         ("ms_bwt_total", C.c_float), ("ms_cse_total", C.c_float), ("ms_total", C.c_float),
         ("ms_cse_narrow", C.c_float), ("cse_rounds_narrow", C.c_uint32), ("ms_radix_kernel", C.c_float),
         ("cse_words", C.c_uint64), ("sort_local_elems", C.c_uint64), ("sort_fallback_elems", C.c_uint64),
+        ("sort_radix_passes", C.c_uint32 * 48),
     ]
 
     def as_dict(self) -> dict:
         d = {}
         for name, _ in self._fields_:
             v = getattr(self, name)
-            if name in ("sort_m", "sort_passes"):
+            if name in ("sort_m", "sort_passes", "sort_radix_passes"):
                 v = [int(x) for x in v][: int(self.sort_rounds)]
             d[name] = v
         return d

@@ -173,9 +173,18 @@ def run_reference(args, rank: int, world: int):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def algorithmic_bytes(st: dict) -> dict:
+def algorithmic_bytes(st: dict, executed: bool = False) -> dict:
+    """SURVEY.md 8d.  P_r is the number of 8-bit digits the keys of round r have to be ordered by (what an LSD
+    radix sort runs; sort_passes).  Rounds >= 1 are sorted tile by tile without radix passes over the working
+    set (csrc/local_sort.cuh); `executed` prices those rounds at what was actually moved instead: one read and
+    one write of the (key, idx) pairs (24 B per element) plus the radix passes of the fall-back elements."""
     n = st["n"]
-    stage_a = 19 * n + sum((44 + 24 * p) * m for m, p in zip(st["sort_m"], st["sort_passes"]))
+    if executed:
+        rp = st.get("sort_radix_passes") or st["sort_passes"]
+        stage_a = 19 * n + sum((44 + 24 * (p if p else 1)) * m for m, p in zip(st["sort_m"], rp))
+        stage_a += 24 * 8 * st.get("sort_fallback_elems", 0)
+    else:
+        stage_a = 19 * n + sum((44 + 24 * p) * m for m, p in zip(st["sort_m"], st["sort_passes"]))
     # emission counted at the bytes actually written: 4 B per packed word (SURVEY.md 8d assumes 20 B raw counts)
     stage_b = 19 * n + 48 * st["cse_visits"] + 4 * st["cse_words"]
     return {"stage_a": stage_a, "stage_b": stage_b, "total": stage_a + stage_b}
@@ -254,6 +263,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peak, peak_src = measured_peak_gbs()
     ab = algorithmic_bytes(st)
+    abx = algorithmic_bytes(st, executed=True)
     radix_ms = st["ms_radix_kernel"] or st["ms_radix"]
     cse_ms = st["ms_cse"]
     if radix_ms >= cse_ms:
@@ -282,7 +292,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "ms_per_launch": k_ms, "note": note,
                 "whole_path": {"algorithmic_bytes": ab["total"], "GBps": ab["total"] / (st["ms_total"] / 1e3) / 1e9,
                                "frac": ab["total"] / (st["ms_total"] / 1e3) / 1e9 / peak,
-                               "stage_a_bytes": ab["stage_a"], "stage_b_bytes": ab["stage_b"]}}
+                               "stage_a_bytes": ab["stage_a"], "stage_b_bytes": ab["stage_b"],
+                               "note": "SURVEY.md 8d formula, P_r = 8-bit digits of the round's keys"},
+                "whole_path_executed": {"algorithmic_bytes": abx["total"],
+                                        "frac": abx["total"] / (st["ms_total"] / 1e3) / 1e9 / peak,
+                                        "note": "rounds sorted tile by tile (no radix passes over the working set) priced "
+                                                "at one read + one write of their pairs plus the fall-back radix passes"}}
 
     gathered = batch.gather_stats(batch.RankStats(args.steps, nbytes * args.steps, 0, st["cse_words"], dev_ms, wall_ms),
                                   device="cuda" if world > 1 else "cpu")
@@ -316,6 +331,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "stage_ms": {k: st[k] for k in ("ms_pack", "ms_radix", "ms_rerank", "ms_rekey", "ms_bwt_gather",
                                             "ms_wavelet", "ms_cse", "ms_bwt_total", "ms_cse_total")},
             "counters": {"sort_rounds": st["sort_rounds"], "sort_m": st["sort_m"], "sort_passes": st["sort_passes"],
+                         "sort_radix_passes": st.get("sort_radix_passes"), "sort_local_elems": st.get("sort_local_elems"),
+                         "sort_fallback_elems": st.get("sort_fallback_elems"),
                          "visits": st["cse_visits"], "emitted_words": st["cse_words"], "cse_rounds": st["cse_rounds"],
                          "peak_frontier": st["cse_peak_frontier"]},
             "roofline": roofline,

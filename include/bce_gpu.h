@@ -83,6 +83,8 @@ typedef struct bce_gpu_stats {
   uint64_t sort_local_elems;     /* elements of rounds >= 1 ordered by the tile-local sort instead of radix passes
                                     (sort_passes[r] then holds the passes an LSD sort of those keys would take) */
   uint64_t sort_fallback_elems;  /* ... of which went through the radix sort after all (groups crossing tiles) */
+  uint32_t sort_radix_passes[48];/* radix passes actually run over the whole working set of round r (0 when the
+                                    tile-local sort took the round) */
 } bce_gpu_stats;
 
 /* ---- lifecycle ---------------------------------------------------------------- */

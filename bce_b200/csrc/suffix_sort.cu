@@ -445,6 +445,8 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
   // the first radix pass of round 0 makes keys and indices from the text itself (BCE_GPU_PACK=1: a
   // separate pack kernel writes them first)
   const bool use_local = !getenv("BCE_GPU_NO_LOCAL_SORT");
+  uint32_t local_min = 1u << 20;           // smaller working sets take the plain radix path (BCE_GPU_LOCAL_MIN: tests)
+  if (const char* v = getenv("BCE_GPU_LOCAL_MIN")) local_min = uint32_t(strtoul(v, nullptr, 10));
   const bool fused_pack = !getenv("BCE_GPU_PACK") && !getenv("BCE_GPU_RADIX_STABLE_FIRST") && !getenv("BCE_GPU_RADIX");
   if (!fused_pack) {
     pack_keys_kernel<<<(n + 256 * PK_ROWS - 1) / (256 * PK_ROWS), 256, 0, st>>>(T, n, keyA, idxA);
@@ -482,7 +484,7 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
       // Rounds >= 1: the groups are short, so tiles are sorted where they are (keys made on the way) and
       // only the groups that cross a tile boundary go through the radix sort (local_sort.cuh)
       uint32_t* gd_cur = gd_next == gdA ? gdB : gdA;
-      if (use_local && m >= (1u << 20)) {
+      if (use_local && m >= local_min) {
         const uint32_t ltiles = (m + LS_TILE - 1) / LS_TILE;
         ls_classify_kernel<<<(ltiles + 255) / 256, 256, 0, st>>>(gd_cur, m, ltiles, lt_pre, lt_suf, lt_cnt);
         ls_scan_kernel<<<1, 1024, 0, st>>>(lt_cnt, ltiles, lt_off, d_totals + 3);

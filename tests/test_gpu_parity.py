@@ -159,3 +159,22 @@ def test_random_small_inputs_archive_parity(frontend):
         data = data.tobytes()
         got = host.compress(frontend, data, threads=1)
         assert got == oracle.compress(data), (trial, n, sigma)
+
+
+def test_tile_local_sort_forced_on_small_inputs(frontend, monkeypatch):
+    """Rounds >= 1 of the suffix sort normally go tile by tile (csrc/local_sort.cuh) only for working sets
+    of 2^20 rotations and more, i.e. never on the inputs the oracle can check.  Forced on everything here:
+    groups crossing tile boundaries (fall-back radix sort + placement), whole-tile groups (bail-out to the
+    radix path), partial last tiles, the index tie-break round of exact powers."""
+    monkeypatch.setenv("BCE_GPU_LOCAL_MIN", "1")
+    for name, data, _ in small_cases() + medium_cases():
+        n = len(data)
+        if n < 2:
+            continue
+        Lo, offo, sao = oracle.bwt(data, want_sa=True)
+        L, off, sa = frontend.bwt(data, want_sa=True)
+        assert off == offo, name
+        assert np.array_equal(np.asarray(sa), np.asarray(sao)), name
+        assert bytes(L) == bytes(Lo), name
+    st = frontend.stats()
+    assert "sort_local_elems" in st

@@ -8,9 +8,10 @@ one synthetic input per GPU.  At N = 1 the workload is the configuration BASELIN
 is quoted on, configs[2]: 1 GB (10^9 bytes) of enwik-shaped synthetic text on a single B200
 (`--workload enwik-100MB` runs configs[1]).  The working set (48 n bytes of keys, indices, SA
 and ranks) exceeds the 126 MB L2 by far, so no L2 flush is needed between steps.
-At N > 1 every rank compresses its own 128 MB file (configs[4]) of the same
-generator (different seeds): replicas only, weak scaling, no data-path collective; one small
-all_gather of per-rank stats is the only traffic.
+At N > 1 every rank compresses its own 1 GB input of the same generator (seed + rank): replicas
+only, weak scaling with the per-GPU work of N = 1, no data-path collective; one small all_gather of
+per-rank stats is the only traffic.  `--workload batch-128MB` runs the 128 MiB
+files of configs[4] instead.
 
 Legs of the default arm:
   value  input resident in HBM when the timed region starts; counts written to HBM.
@@ -367,7 +368,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload is None:
-        args.workload = "enwik-1GB" if world == 1 else "batch-128MB"
+        # weak scaling: every GPU compresses its own 1 GB input (seed + rank), the configuration the metric is
+        # quoted on, at every N -- so that the per-N values are comparable.  BASELINE's batch configuration
+        # (128 MiB files) is `--workload batch-128MB`.
+        args.workload = "enwik-1GB"
 
     if args.impl == "reference":
         return run_reference(args, rank, world)

@@ -6,7 +6,10 @@
 // learns where its digit runs start in the output through a chained scan over tiles
 // (decoupled look-back on tagged descriptors, common.cuh), and writes keys and values
 // out of a shared-memory staging buffer so that every digit run is a coalesced burst.
-// Digit histograms for all passes of one sort come from one extra read of the keys.
+// The first pass of a sort needs no stability and runs without chained scan and stable ranking
+// (radix_unordered_kernel); in round 0 of the suffix sort it also makes the keys from the text.
+// Digit histograms come from a RadixHistSource where the caller has one (the text's byte histogram,
+// counts taken by the kernel that wrote the keys), else from one extra read of the keys.
 //
 // HBM traffic per pass: read 12 B + write 12 B per element  (24 m P_r).
 #include <math.h>

@@ -6,17 +6,20 @@
 // of T with row 0 = least rotation and offset = its start index.  Here all n rotations
 // are sorted directly by prefix doubling over packed rank keys:
 //
-//   round 0   key(i) = 8 bytes T[i..i+8) (cyclic, big-endian); LSD radix sort of (key, i)
+//   round 0   key(i) = 8 bytes T[i..i+8) (cyclic, big-endian); LSD radix sort of (key, i); the first
+//             pass makes the keys from the text and is unordered (radix_sort.cu)
 //   re-rank   rank[i] = SA position of the head of i's group; rotations alone in their
 //             group are final and leave the working set
-//   round r   key = (dense group id << 32) | rank[(i + h) mod n], h = 8 * 2^(r-1);
-//             radix sort of the working set; groups stay where they are, so the list slot
-//             of an element fixes its SA position
+//   round r   key = (dense group id << 32) | rank[(i + h) mod n], h = 8 * 2^(r-1); the groups are
+//             short, so the working set is sorted tile by tile (local_sort.cuh; the tile sort makes
+//             its keys itself) and only groups that cross a tile boundary are radix-sorted;
+//             groups stay where they are, so the list slot of an element fixes its SA position
 //   end       working set empty, or h >= n (T is a power w^k: remaining ties are identical
 //             rotations, ordered by index so that offset is the smallest one)
 //
-// Kernels: K1 pack, K2 radix pass (radix_sort.cu), K3 re-rank + stable compaction
-// (single pass, chained scan), K4 key rebuild (gather-bound), K5 BWT gather (gather-bound).
+// Kernels here: K1 pack (only without the fused first pass), K3 re-rank + stable compaction + binned rank
+// pairs (single pass, chained scans), K3b rank scatter, K4 key rebuild with digit histograms (radix path
+// of small or declined rounds), K5 BWT gather.
 #include <stdlib.h>
 
 #include <algorithm>

@@ -68,7 +68,8 @@ struct CseArgs {
   uint32_t* fb[2][8];                    //   x1
   uint32_t cap;                          // nodes per frontier buffer, multiple of 4
   uint32_t* emit[8];                     // emission buffers (words)
-  unsigned long long ecap[8];            // their capacity in words
+  unsigned long long ecap[8];            // their capacity in words (no round may start that could overflow it)
+  unsigned long long esoft[8];           // batch target: once a stream holds this many words the batch ends with the round
   uint64_t* desc;                        // 3 x desc_tiles
   uint32_t desc_tiles;
   uint32_t max_rounds;
@@ -266,7 +267,7 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(THREADS, 1) cse_narr
         const uint32_t cnt = sh.all_cnt[p][k];
         total += cnt;
         widest = max(widest, cnt);
-        if (sh.all_emitted[p][k] + (unsigned long long)cnt * maxw > a.ecap[k]) drain = 1;
+        if (sh.all_emitted[p][k] + (unsigned long long)cnt * maxw > a.ecap[k] || sh.all_emitted[p][k] >= a.esoft[k]) drain = 1;
       }
       sh.decision = total == 0 ? kCseDone
                   : round >= a.round_limit ? kCseRunaway
@@ -441,7 +442,7 @@ __global__ void __launch_bounds__(256, 1) cse_tiny_kernel(CseArgs a) {
         const uint32_t cnt = sh.cz[p][k] + sh.co[p][k];
         total += cnt;
         widest = max(widest, cnt);
-        if (sh.emitted[p][k] + (unsigned long long)cnt * maxw > a.ecap[k]) drain = 1;
+        if (sh.emitted[p][k] + (unsigned long long)cnt * maxw > a.ecap[k] || sh.emitted[p][k] >= a.esoft[k]) drain = 1;
       }
       status = total == 0 ? kCseDone
              : round >= a.round_limit ? kCseRunaway
@@ -637,9 +638,13 @@ int cse_begin(Ctx* c, uint32_t n) {
     for (int l = 0; l < 8; ++l) H->emit_dev[s][l] = cv.take<uint32_t>(ew);
   if (!cv.ok()) { set_error(c, "cse_begin: scratch carve failed (need %zu)", need); return BCE_GPU_E_NOMEM; }
   H->ecap_words = ew;
-  H->batch_words = c->cse_resident ? ew : std::min(ew, std::max(batch_bytes / 32, size_t(1) << 16));
+  // per-stream target: the streams are uneven (the largest carries about a third of the words), so a third of the
+  // batch's words per stream makes batches of about batch_bytes in all
+  H->batch_words = c->cse_resident ? ew : std::min(ew, std::max(batch_bytes / 12, size_t(1) << 16));
   H->fill_set = 0;
-  for (int l = 0; l < 8; ++l) { a.emit[l] = H->emit_dev[0][l]; a.ecap[l] = H->batch_words; }
+  // the worst case (every node emits its widest count) is checked against the whole device buffer; the batch
+  // size is a target that the words actually emitted are compared with (a round emits ~0.2 words per node)
+  for (int l = 0; l < 8; ++l) { a.emit[l] = H->emit_dev[0][l]; a.ecap[l] = ew; a.esoft[l] = H->batch_words; }
   const size_t words = size_t(n) / 32 + 1;
   for (int l = 0; l < 8; ++l) { a.ranks[l] = c->ranks.as<uint64_t>() + size_t(l) * words; a.C[l] = c->C[l]; }
   a.cap = uint32_t(cap);
@@ -845,7 +850,7 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
     // for any round) and go on -- nothing was processed, no state is lost
     if (H->batch_words < H->ecap_words) {
       H->batch_words = std::min(H->ecap_words, H->batch_words * 2);
-      for (int l = 0; l < 8; ++l) H->args.ecap[l] = H->batch_words;
+      for (int l = 0; l < 8; ++l) H->args.esoft[l] = H->batch_words;
       BCE_TRACE("cse: batch size raised to %zu words per stream", H->batch_words);
       cse_reset_emitted_kernel<<<1, 32, 0, st>>>(H->args.st);
       c->stats.gpu_launches++;

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
         }
         nodes += lvl;
         widest = max(widest, uint32_t(min(lvl, 0xFFFFFFFFull)));
-        if (s_emitted[l] + lvl * max_words(a) > a.ecap[l]) drain = 1;   // a round emits at most one count per node
+        if (s_emitted[l] + lvl * max_words(a) > a.ecap[l] || s_emitted[l] >= a.esoft[l]) drain = 1;   // a round emits at most one count per node
       }
       // tiles per level, ascending, and the number of tiles scheduled before every breakpoint
       for (int l = 0; l < 8; ++l) s_lt[l] = (s_cnt[l][0] + TILE - 1) / TILE + (s_cnt[l][1] + TILE - 1) / TILE;

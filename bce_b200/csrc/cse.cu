@@ -640,7 +640,9 @@ int cse_begin(Ctx* c, uint32_t n) {
   H->ecap_words = ew;
   // per-stream target: the streams are uneven (the largest carries about a third of the words), so a third of the
   // batch's words per stream makes batches of about batch_bytes in all
-  H->batch_words = c->cse_resident ? ew : std::min(ew, std::max(batch_bytes / 12, size_t(1) << 16));
+  // ... and never more than a third of a word per input byte, so that a smaller input still leaves in a
+  // handful of batches whose copies overlap the kernels (the whole emission is ~1.6 words per byte)
+  H->batch_words = c->cse_resident ? ew : std::min(ew, std::max(std::min(batch_bytes / 12, size_t(n) / env_size("BCE_GPU_BATCH_DIV", 3)), size_t(1) << 16));
   H->fill_set = 0;
   // the worst case (every node emits its widest count) is checked against the whole device buffer; the batch
   // size is a target that the words actually emitted are compared with (a round emits ~0.2 words per node)

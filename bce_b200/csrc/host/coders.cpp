@@ -148,7 +148,7 @@ void ContextModel::configure(const std::array<uint8_t, kConfigCols>& bits) {
   off_.fill(0);
   for (uint32_t k = 2; k < uint32_t(kConfigCols); ++k) {
     off_[k] = start | (uint32_t(bits[k]) << 24);
-    start += k << (bits[k] * 2);
+    start += (k + 2) << (bits[k] * 2);      // k counters + their 16-bit sum per row
   }
   stat_.assign(start, 0);
 }
@@ -173,7 +173,7 @@ void StreamEncoder::count(uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2, ui
   uint8_t* row = model_.row(k, c1, c2, cs);
   uint32_t below = sym, total = k;                                  // bce.cpp:514-518
   for (uint32_t i = 0; i < sym; ++i) below += row[i];
-  for (uint32_t i = 0; i < k; ++i) total += row[i];
+  total += ContextModel::sum(row, k);
   rc_.put(below, uint32_t(row[sym]) + 1, total);
   ContextModel::bump(row, k, sym);
 }
@@ -189,7 +189,7 @@ void StreamEncoder::packed(const uint32_t* words, size_t count) {
     uint8_t* row = model_.row_at(k, ctx);
     uint32_t below = sym, total = k;                                // bce.cpp:514-518
     for (uint32_t j = 0; j < sym; ++j) below += row[j];
-    for (uint32_t j = 0; j < k; ++j) total += row[j];
+    total += ContextModel::sum(row, k);
     rc_.put(below, uint32_t(row[sym]) + 1, total);
     ContextModel::bump(row, k, sym);
   }
@@ -237,7 +237,7 @@ uint32_t StreamDecoder::count(uint32_t k, uint32_t c1, uint32_t c2, uint32_t cs)
   }
   uint8_t* row = model_.row(k, c1, c2, cs);
   uint32_t total = k;
-  for (uint32_t i = 0; i < k; ++i) total += row[i];
+  total += ContextModel::sum(row, k);
   const uint32_t sym = rd_.get(row, k, total);
   ContextModel::bump(row, k, sym);
   return sym;

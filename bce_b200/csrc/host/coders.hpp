@@ -68,17 +68,26 @@ class RangeDecoder {
 class ContextModel {
  public:
   void configure(const std::array<uint8_t, kConfigCols>& bits);   // bce.cpp:700-705
-  // counters of the context (k, c1, c2, cs); uint32 wrap-around as in bce.cpp:674
+  // counters of the context (k, c1, c2, cs); uint32 wrap-around as in bce.cpp:674.
+  // A row is k one-byte counters followed by their sum as a uint16 (kept up to date by bump), so that a
+  // symbol costs one load for the total instead of k adds; the layout is internal, the counters and every
+  // coded interval are the reference's.
   uint8_t* row(uint32_t k, uint32_t c1, uint32_t c2, uint32_t cs) {
     const uint32_t o = off_[k], b = o >> 24;
     const uint32_t ctx = (((c1 << b) / cs) << b) | ((c2 << b) / cs);
-    return stat_.data() + (o & 0x00FFFFFFu) + size_t(ctx) * k;
+    return stat_.data() + (o & 0x00FFFFFFu) + size_t(ctx) * (k + 2);
   }
   // same counters addressed by a context index computed elsewhere (packed device words)
-  uint8_t* row_at(uint32_t k, uint32_t ctx) { return stat_.data() + (off_[k] & 0x00FFFFFFu) + size_t(ctx) * k; }
+  uint8_t* row_at(uint32_t k, uint32_t ctx) { return stat_.data() + (off_[k] & 0x00FFFFFFu) + size_t(ctx) * (k + 2); }
+  static uint32_t sum(const uint8_t* row, uint32_t k) { return uint32_t(row[k]) | (uint32_t(row[k + 1]) << 8); }
   static void bump(uint8_t* row, uint32_t k, uint32_t sym) {      // bce.cpp:531-533
-    if (++row[sym] == 0xFF)
-      for (uint32_t i = 0; i < k; ++i) row[i] >>= 1;
+    uint32_t s = sum(row, k) + 1;
+    if (++row[sym] == 0xFF) {
+      s = 0;
+      for (uint32_t i = 0; i < k; ++i) { row[i] >>= 1; s += row[i]; }
+    }
+    row[k] = uint8_t(s);
+    row[k + 1] = uint8_t(s >> 8);
   }
   size_t table_bytes() const { return stat_.size(); }
 

@@ -21,7 +21,7 @@ CSRC = PKG / "csrc"
 HOST = CSRC / "host"
 
 GPU_SOURCES = ["api.cu", "radix_sort.cu", "suffix_sort.cu", "wavelet.cu", "cse.cu", "unbwt.cu"]
-GPU_HEADERS = ["common.cuh", "ctx.h", "cse_wide.cuh", "radix_chunked.cuh", "local_sort.cuh", "../../include/bce_gpu.h"]
+GPU_HEADERS = ["common.cuh", "ctx.h", "cse_wide.cuh", "local_sort.cuh", "../../include/bce_gpu.h"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -64,13 +64,26 @@ def _run(cmd, cwd=None):
     return r
 
 
+def _flavor() -> str:
+    """`BCE_GPU_EXPERIMENTS=1 python -m bce_b200.build` compiles the development switches in (environment knobs
+    for A/B timing, the round-1 kernels kept for comparison, bce_gpu_dbg_radix).  The default build -- the
+    one __graft_entry__.build() and the tests use -- has none of them."""
+    return "experiments" if os.environ.get("BCE_GPU_EXPERIMENTS", "") not in ("", "0") else "default"
+
+
 def build_gpu(force: bool = False, verbose: bool = False) -> Path:
     deps = [CSRC / s for s in GPU_SOURCES] + [CSRC / h for h in GPU_HEADERS]
-    if force or _stale(LIB_GPU, deps):
+    stamp = PKG / "_build" / "gpu_flavor.txt"
+    flavor = _flavor()
+    if force or _stale(LIB_GPU, deps) or not stamp.exists() or stamp.read_text().strip() != flavor:
         cmd = [_nvcc(), *NVCC_FLAGS, "-ccbin", _cxx(), "-shared", "-o", LIB_GPU, *GPU_SOURCES]
+        if flavor == "experiments":
+            cmd[1:1] = ["-DBCE_GPU_EXPERIMENTS"]
         if verbose:
             cmd[1:1] = ["-Xptxas", "-v"]
         r = _run(cmd, cwd=CSRC)
+        stamp.parent.mkdir(exist_ok=True)
+        stamp.write_text(flavor + "\n")
         if verbose:
             print(r.stderr)
     return LIB_GPU

@@ -9,9 +9,13 @@
 
 namespace bce {
 
-bool trace_on() {
+// BCE_GPU_TRACE=1: launch-by-launch timing on stderr (diagnostics only; read once per API call, never
+// on a launch path)
+static bool g_trace = false;
+bool trace_on() { return g_trace; }
+static void refresh_trace() {
   const char* v = getenv("BCE_GPU_TRACE");
-  return v && *v && *v != '0';
+  g_trace = v && *v && *v != '0';
 }
 
 void set_error(Ctx* c, const char* fmt, ...) {
@@ -152,6 +156,7 @@ static int check_n(Ctx* c, uint32_t n) {
 }
 
 static void begin_call(Ctx* c) {
+  refresh_trace();
   c->err[0] = 0;
   cudaSetDevice(c->device);
 }
@@ -245,6 +250,7 @@ int bce_gpu_open(int device, bce_gpu_ctx** out) {
             cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
   for (int i = 0; ok && i < 256; ++i) ok = cudaEventCreate(&c->pass_ev[i]) == cudaSuccess;
+  if (ok) ok = bce::radix_init_device(c) == BCE_GPU_OK;      // per-device function attributes
   if (ok) ok = c->small.ensure(c, bce::kSmallBytes) == BCE_GPU_OK;
   if (ok) ok = c->pinned_small.ensure(c, bce::kSmallBytes) == BCE_GPU_OK;
   if (ok) ok = cudaStreamSynchronize(c->stream) == cudaSuccess;
@@ -260,7 +266,7 @@ void bce_gpu_close(bce_gpu_ctx* h) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   bce::cse_destroy(c);
   c->text.release(); c->bwt.release(); c->ranks.release(); c->scratch.release();
-  c->small.release(); c->desc.release(); c->radix_tmp.release();
+  c->small.release(); c->desc.release();
   c->pinned_small.release(); c->pinned_emit.release(); c->pinned_io.release();
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->pass_ev) if (e) cudaEventDestroy(e);
@@ -283,6 +289,22 @@ int bce_gpu_set_scratch_limit(bce_gpu_ctx* h, size_t bytes) {
   if (!h) return BCE_GPU_E_ARG;
   static_cast<Ctx*>(h)->scratch_limit = bytes;
   return BCE_GPU_OK;
+}
+
+int bce_gpu_set_option(bce_gpu_ctx* h, int option, uint64_t value) {
+  if (!h) return BCE_GPU_E_ARG;
+  Ctx* c = static_cast<Ctx*>(h);
+  switch (option) {
+    case BCE_GPU_OPT_EMIT_BATCH_BYTES:
+      c->emit_batch_bytes = value ? size_t(value) : size_t(1) << 30;
+      return BCE_GPU_OK;
+    case BCE_GPU_OPT_LOCAL_SORT_MIN:
+      c->local_sort_min = value ? uint32_t(value > 0xFFFFFFFFull ? 0xFFFFFFFFull : value) : 1u << 20;
+      return BCE_GPU_OK;
+    default:
+      set_error(c, "bce_gpu_set_option: unknown option %d", option);
+      return BCE_GPU_E_ARG;
+  }
 }
 
 int bce_gpu_bwt(bce_gpu_ctx* h, const uint8_t* T, uint32_t n, uint8_t* L_out, uint32_t* offset_out,

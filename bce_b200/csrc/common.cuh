@@ -68,10 +68,6 @@ struct Carver {
   static size_t need(size_t count, size_t elem) { return (count * elem + 255) & ~size_t(255); }
 };
 
-struct StageTimer {   // CUDA-event stopwatch on the context stream, accumulates into a float
-  cudaEvent_t a = nullptr, b = nullptr;
-};
-
 // ---------------------------------------------------------------------------------
 // device side
 // ---------------------------------------------------------------------------------
@@ -161,25 +157,6 @@ __device__ __forceinline__ uint32_t lookback_serial(uint64_t* desc, uint32_t str
   return excl;
 }
 
-// Same, for the "most recent non-zero value" operator (carry of the last group head).
-__device__ __forceinline__ uint32_t lookback_serial_last(uint64_t* desc, uint32_t stride, uint32_t tile,
-                                                         uint32_t tag, uint32_t agg, uint32_t* err) {
-  if (tile == 0) {
-    desc_store(desc, desc_pack(tag, kDescPrefix, agg));
-    return 0;
-  }
-  // a tile that contains a head already knows its inclusive value
-  desc_store(desc + size_t(tile) * stride, desc_pack(tag, agg ? kDescPrefix : kDescAgg, agg));
-  uint32_t excl = 0;
-  for (uint32_t t = tile; t-- > 0;) {
-    uint64_t w = desc_wait(desc + size_t(t) * stride, tag, err);
-    if (uint32_t(w) != 0) { excl = uint32_t(w); break; }
-    if (desc_status(w) == kDescPrefix) break;
-  }
-  if (!agg) desc_store(desc + size_t(tile) * stride, desc_pack(tag, kDescPrefix, excl));
-  return excl;
-}
-
 // Warp-wide look-back over a chain of tiles [first, tile): all 32 lanes must call it.
 // Returns (to every lane) the exclusive prefix and publishes the inclusive one.
 __device__ __forceinline__ uint32_t lookback_warp(uint64_t* desc, uint32_t tile, uint32_t first,
@@ -243,57 +220,12 @@ __device__ __forceinline__ uint32_t lookback_warp_max(uint64_t* desc, uint32_t t
   return excl;
 }
 
-// Wide-window variant of lookback_warp: every lane fetches B predecessor descriptors per
-// step (B independent loads in flight), so one step covers 32*B tiles.  A persistent kernel
-// runs gridDim tiles of the same phase at once; none of them has an inclusive prefix yet, so
-// the walk has to get past all of them -- the window is what bounds the number of serial
-// L2 round trips.
-template <int B>
-__device__ __forceinline__ uint32_t lookback_warp_wide(uint64_t* desc, uint32_t tile, uint32_t first,
-                                                       uint32_t tag, uint32_t agg, uint32_t* err) {
-  const unsigned lane = lane_id();
-  if (tile == first) {
-    if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescPrefix, agg));
-    return 0;
-  }
-  if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescAgg, agg));
-  uint32_t excl = 0;
-  int64_t base = int64_t(tile) - 1;
-  for (;;) {
-    uint64_t w[B];
-#pragma unroll
-    for (int k = 0; k < B; ++k) {
-      const int64_t t = base - (k * 32 + int(lane));
-      w[k] = t >= int64_t(first) ? desc_load(desc + t) : desc_pack(tag, kDescPrefix, 0);
-    }
-#pragma unroll
-    for (int k = 0; k < B; ++k) {
-      const int64_t t = base - (k * 32 + int(lane));
-      if (t >= int64_t(first) && desc_tag(w[k]) != (tag & 0x3FFFFFFFu)) w[k] = desc_wait(desc + t, tag, err);
-    }
-    bool done = false;
-#pragma unroll
-    for (int k = 0; k < B; ++k) {
-      if (!done) {
-        const unsigned pm = __ballot_sync(0xffffffffu, desc_status(w[k]) == kDescPrefix);
-        uint32_t v = uint32_t(w[k]);
-        if (pm) {
-          const unsigned stop = __ffs(pm) - 1;
-          if (lane > stop) v = 0;
-          done = true;
-        }
-        excl += __reduce_add_sync(0xffffffffu, v);
-      }
-    }
-    if (done) break;
-    base -= 32 * B;
-  }
-  if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescPrefix, excl + agg));
-  return excl;
-}
-
-// The second half of lookback_warp_wide for callers that published their aggregate earlier
-// (tile != first): walk the predecessors, return the exclusive prefix, publish the inclusive one.
+// Wide-window look-back, second half: the caller has published its aggregate (tile != first); walk
+// the predecessors, return the exclusive prefix, publish the inclusive one.  Every lane fetches B
+// predecessor descriptors per step (B independent loads in flight), so one step covers 32*B tiles.
+// A persistent kernel runs gridDim tiles of the same phase at once; none of them has an inclusive
+// prefix yet, so the walk has to get past all of them -- the window is what bounds the number of
+// serial L2 round trips.
 template <int B>
 __device__ __forceinline__ uint32_t lookback_resolve_wide(uint64_t* desc, uint32_t tile, uint32_t first,
                                                           uint32_t tag, uint32_t agg, uint32_t* err) {
@@ -331,6 +263,18 @@ __device__ __forceinline__ uint32_t lookback_resolve_wide(uint64_t* desc, uint32
   }
   if (lane == 0) desc_store(desc + tile, desc_pack(tag, kDescPrefix, excl + agg));
   return excl;
+}
+
+// Publish the aggregate, then resolve: the whole chained-scan step of one tile.
+template <int B>
+__device__ __forceinline__ uint32_t lookback_warp_wide(uint64_t* desc, uint32_t tile, uint32_t first,
+                                                       uint32_t tag, uint32_t agg, uint32_t* err) {
+  if (tile == first) {
+    if (lane_id() == 0) desc_store(desc + tile, desc_pack(tag, kDescPrefix, agg));
+    return 0;
+  }
+  if (lane_id() == 0) desc_store(desc + tile, desc_pack(tag, kDescAgg, agg));
+  return lookback_resolve_wide<B>(desc, tile, first, tag, agg, err);
 }
 
 // Block-wide exclusive scan of one value per thread (THREADS multiple of 32, <= 1024).

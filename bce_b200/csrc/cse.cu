@@ -77,7 +77,7 @@ struct CseArgs {
   uint32_t use_narrow;                   // 1 = hand narrow frontiers to the cluster kernels
   uint32_t narrow_enter;                 // ... once every level holds at most this many nodes
   uint32_t use_tiny, tiny_enter;         // 1 = the one-CTA kernel takes frontiers of <= tiny_enter nodes per level
-  uint32_t dbg;                          // timing experiments only (results become wrong): 1 no look-back, 2 no gathers, 4 no flush
+  uint32_t dbg;                          // experiment builds only (results become wrong): 1 no look-back, 2 no gathers, 4 no flush
   uint32_t emit_mode;                    // kEmitRaw / kEmitCoder / kEmitScan
   unsigned long long min_nodes, max_nodes;   // wide kernel: leave (kCseGoWide) when the frontier is outside
   uint8_t cfgbits[8][32];                // kEmitCoder: context bits per (stream, k), bce.cpp:713-724
@@ -582,13 +582,10 @@ struct CseHost {
   int last_grid = 0;                     // grid size of the previous wide launch (0 = none since cse_begin)
   bool tail_cut = false;                 // hosted emission: the batch was already cut where the frontier collapsed
   bool finished = false;                 // the level loop terminated
+  uint32_t desc_epoch = 0;               // round >> 29 at which the descriptors were last cleared
 };
 
-static size_t env_size(const char* name, size_t dflt) {
-  const char* v = getenv(name);
-  if (!v || !*v) return dflt;
-  return size_t(strtoull(v, nullptr, 10));
-}
+static size_t env_size(const char* name, size_t dflt) { return exp_env(name, dflt); }   // experiment builds only
 
 void cse_destroy(Ctx* c) {
   delete c->cse;
@@ -619,7 +616,7 @@ int cse_begin(Ctx* c, uint32_t n) {
   H->sets = (c->cse_resident || env_size("BCE_GPU_NO_OVERLAP", 0)) ? 1 : 2;
   // words handed back per batch and stream: small batches let the copy of batch k overlap the
   // kernels of batch k+1 (two pinned buffers of this size alternate)
-  const size_t batch_bytes = env_size("BCE_GPU_PINNED_LIMIT", size_t(1) << 30);
+  const size_t batch_bytes = c->emit_batch_bytes;          // BCE_GPU_OPT_EMIT_BATCH_BYTES
   size_t ew = size_t(n) * wmax;                              // a level emits at most n-1 counts in total
   const size_t per_level_min = (cap + CS_MAX_TILE) * wmax;   // one round must always fit
   if (ew * 8 * 4 * H->sets > left) ew = left / (8 * 4 * H->sets);
@@ -665,16 +662,12 @@ int cse_begin(Ctx* c, uint32_t n) {
   a.tiny_enter = kTinyEnter;
   if (a.use_tiny) H->narrow = 2;         // the roots are one node per level
   a.narrow_enter = H->use_medium ? kMediumEnter : kNarrowEnter;
-  {
-    static bool attr_done = false;
-    if (!attr_done) {
-      BCE_CUDA(c, cudaFuncSetAttribute(cse_narrow_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       int(sizeof(NarrowShared<1024, 1>))));
-      BCE_CUDA(c, cudaFuncSetAttribute(cse_narrow_kernel<NM_THREADS, NM_K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       int(sizeof(NarrowShared<NM_THREADS, NM_K>))));
-      attr_done = true;
-    }
-  }
+  // function attributes are per device: set for this context's device on every run (a process may hold
+  // contexts on several GPUs)
+  BCE_CUDA(c, cudaFuncSetAttribute(cse_narrow_kernel<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   int(sizeof(NarrowShared<1024, 1>))));
+  BCE_CUDA(c, cudaFuncSetAttribute(cse_narrow_kernel<NM_THREADS, NM_K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   int(sizeof(NarrowShared<NM_THREADS, NM_K>))));
   H->last_round = 0;
   H->known_nodes = 0;
   H->pending = H->pending_done = H->finished = false;
@@ -685,6 +678,7 @@ int cse_begin(Ctx* c, uint32_t n) {
   H->fixed_items = (items == 2 || items == 4) ? items : 0;
 
   BCE_CUDA(c, cudaMemsetAsync(a.desc, 0, 3 * desc_tiles * sizeof(uint64_t), st));
+  H->desc_epoch = 0;
   cse_init_kernel<<<1, 32, 0, st>>>(a, n);
   c->stats.gpu_launches++;
   BCE_CUDA(c, cudaGetLastError());
@@ -695,7 +689,7 @@ int cse_begin(Ctx* c, uint32_t n) {
     const void* f4 = packed ? (const void*)cse_wide_kernel<4, 2> : (const void*)cse_wide_kernel<4, 5>;
     const size_t s2 = packed ? 2 * sizeof(WideStage<2, 2>) : 2 * sizeof(WideStage<2, 5>);
     const size_t s4 = packed ? 2 * sizeof(WideStage<4, 2>) : 2 * sizeof(WideStage<4, 5>);
-    if (H->var_fn[0] != f2) {
+    {
       int p2 = 0, p4 = 0;
       BCE_CUDA(c, cudaFuncSetAttribute(f2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s2)));
       BCE_CUDA(c, cudaFuncSetAttribute(f4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s4)));
@@ -726,15 +720,17 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
     if (hops > 100000) { set_error(c, "cse: wide/narrow ping-pong"); return BCE_GPU_E_INTERNAL; }
     const bool was_narrow = H->narrow != 0;
     BCE_CUDA(c, cudaEventRecord(c->ev[0], st));
+    H->args.max_rounds = 0x7FFFFFFFu;
+    H->args.dbg = 0;
+#ifdef BCE_GPU_EXPERIMENTS
     {   // timing experiments (BCE_GPU_CSE_DBG_ROUND / _FLAGS): run one chosen round with parts off
       const uint32_t dbg_round = uint32_t(env_size("BCE_GPU_CSE_DBG_ROUND", 0));
-      H->args.max_rounds = 0x7FFFFFFFu;
-      H->args.dbg = 0;
       if (dbg_round && !H->narrow) {
         if (H->last_round < dbg_round) H->args.max_rounds = dbg_round - H->last_round;
         else if (H->last_round == dbg_round) { H->args.max_rounds = 1; H->args.dbg = uint32_t(env_size("BCE_GPU_CSE_DBG_FLAGS", 0)); }
       }
     }
+#endif
     if (H->narrow == 2) {
       cse_tiny_kernel<<<1, 256, 0, st>>>(H->args);
       BCE_CUDA(c, cudaGetLastError());
@@ -771,6 +767,10 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
       if (grid != H->last_grid) {
         if (H->last_grid) { cse_reset_barrier_kernel<<<1, 1, 0, st>>>(H->args.st); c->stats.gpu_launches++; }
         H->last_grid = grid;
+      }
+      if ((H->last_round >> 29) != H->desc_epoch) {   // 30-bit tags: no descriptor older than 2^29 rounds may survive
+        BCE_CUDA(c, cudaMemsetAsync(H->args.desc, 0, 3 * size_t(H->args.desc_tiles) * sizeof(uint64_t), st));
+        H->desc_epoch = H->last_round >> 29;
       }
       void* kargs[] = {&H->args};
       BCE_CUDA(c, cudaLaunchCooperativeKernel(H->var_fn[v], dim3(grid), dim3(CS_THREADS), kargs,

@@ -22,6 +22,13 @@
 // the same time are links of 8 different chains rather than consecutive links of one.
 #pragma once
 
+// timing experiments (parts of the kernel switched off, results wrong) exist in experiment builds only
+#ifdef BCE_GPU_EXPERIMENTS
+#define CSE_DBG(a) ((a).dbg)
+#else
+#define CSE_DBG(a) 0u
+#endif
+
 namespace bce {
 
 // EW = most words one count can take: 5 (raw bce_tuple) or 2 (packed modes); it sizes the staging
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
       uint32_t o0;
       locate(tile, 0u, l, hh, nv, o0, tj);
       load_nodes(l, hh, nv, o0);
-      gather(l, (a.dbg & 2u) ? 0 : nv);
+      gather(l, (CSE_DBG(a) & 2u) ? 0 : nv);
     }
 
     while (have || p_valid) {
@@ -290,14 +297,14 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
       if (p_valid && warp < 3) {
         const uint32_t agg = warp == 0 ? p_tz : (warp == 1 ? p_to : p_te);
         uint32_t pre = 0;
-        if (a.dbg & 1u) pre = (p_desc - p_first) * uint32_t(TILE) / 2u;
+        if (CSE_DBG(a) & 1u) pre = (p_desc - p_first) * uint32_t(TILE) / 2u;
         else if (p_desc != p_first)
           pre = lookback_resolve_wide<4>(a.desc + size_t(warp) * a.desc_tiles, p_desc, p_first, tag, agg, &S->err);
         if (lane == 0) s_prefix[warp] = pre;
       }
       __syncthreads();          // staged outputs (both buffers) and prefixes are visible to everyone
       // ---- gather(i+1) ----------------------------------------------------------------------------
-      if (have_next) gather(l2, (a.dbg & 2u) ? 0 : nv2);
+      if (have_next) gather(l2, (CSE_DBG(a) & 2u) ? 0 : nv2);
       // ---- flush(i-1) -------------------------------------------------------------------------------
       if (p_valid) {
         const WideStage<ITEMS, EW>& st = stage[buf ^ 1];
@@ -307,7 +314,7 @@ __global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
         uint32_t* __restrict__ gs = a.fs[nxt][ln];
         uint32_t* __restrict__ ga = a.fa[nxt][ln];
         uint32_t* __restrict__ gb = a.fb[nxt][ln];
-        const uint32_t fl = (a.dbg & 4u) ? 0u : 1u;
+        const uint32_t fl = (CSE_DBG(a) & 4u) ? 0u : 1u;
         for (uint32_t j = tid; j < p_tz * fl; j += CS_THREADS) {
           const uint32_t at = pz + j;
           if (at < a.cap) { gs[at] = st.zs[j]; ga[at] = st.za[j]; gb[at] = st.zb[j]; }

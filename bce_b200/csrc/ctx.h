@@ -1,6 +1,8 @@
 // ctx.h -- the context behind bce_gpu_ctx and the internal stage entry points.
 #pragma once
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 struct bce_gpu_ctx {};   // opaque to callers; bce::Ctx derives from it
@@ -8,6 +10,19 @@ struct bce_gpu_ctx {};   // opaque to callers; bce::Ctx derives from it
 namespace bce {
 
 constexpr int kMaxSortRounds = 48;
+
+// Knobs read from the environment exist only in experiment builds (-DBCE_GPU_EXPERIMENTS, see
+// bce_b200/build.py); the shipped library takes every such decision from the defaults measured in
+// profiles/ and never calls getenv on a launch path.
+inline size_t exp_env(const char* name, size_t dflt) {
+#ifdef BCE_GPU_EXPERIMENTS
+  const char* v = getenv(name);
+  if (v && *v) return size_t(strtoull(v, nullptr, 10));
+#else
+  (void)name;
+#endif
+  return dflt;
+}
 
 struct CseDeviceState;   // cse.cu
 
@@ -30,13 +45,16 @@ struct Ctx : bce_gpu_ctx {
   DevBuf scratch;     // carved per stage
   DevBuf small;       // counters, histograms, descriptors' tickets, state structs
   DevBuf desc;        // tile descriptors (tagged, never cleared between passes)
-  DevBuf radix_tmp;   // per-chunk digit histograms / offsets of the chunked radix pass
   PinnedBuf pinned_small;   // host mirror for small read-backs
   PinnedBuf pinned_emit;    // emitted counts handed to the caller (two buffers alternate)
   PinnedBuf pinned_emit2;
   PinnedBuf pinned_io;      // staging for pageable caller buffers
 
   uint32_t desc_tag = 0;    // monotonically increasing pass tag (30 bits used)
+
+  // options (bce_gpu_set_option)
+  size_t emit_batch_bytes = size_t(1) << 30;   // BCE_GPU_OPT_EMIT_BATCH_BYTES
+  uint32_t local_sort_min = 1u << 20;          // BCE_GPU_OPT_LOCAL_SORT_MIN
 
   // state of the current input
   uint32_t n = 0;
@@ -109,8 +127,7 @@ int unbwt_run(Ctx* c, uint32_t offset, uint32_t n, uint8_t* out_host);
 int next_tag(Ctx* c);
 int h2d(Ctx* c, void* dst, const void* src, size_t bytes);
 int d2h(Ctx* c, void* dst, const void* src, size_t bytes);
-void tic(Ctx* c);
-float toc(Ctx* c);   // ms since tic on ctx->stream (synchronises the stream)
+int radix_init_device(Ctx* c);   // radix_sort.cu: per-device function attributes
 size_t scratch_budget(Ctx* c);
 
 }  // namespace bce

@@ -36,6 +36,14 @@ bool slurp(const std::string& path, std::vector<uint8_t>& out) {        // File:
   return size == 0 || bool(f.read(reinterpret_cast<char*>(out.data()), size));
 }
 
+// The format carries n as a varint of at most 31 binary digits (bce.cpp:372-377) and every index is a
+// uint32: the reference silently wraps on larger files, this tool refuses them.
+bool too_large(const std::vector<uint8_t>& data) {
+  if (data.size() <= 0x7FFFFFFFull) return false;
+  std::printf("File too large: %" PRIuMAX " B (the BCE v0.4 format holds at most 2147483647 B)\n", uintmax_t(data.size()));
+  return true;
+}
+
 int gpu_failure(bce_gpu_ctx* ctx, int rc) {
   std::printf("GPU front end failed: %s (%s)\n", bce_gpu_error_string(rc), ctx ? bce_gpu_last_error(ctx) : "no context");
   return rc;
@@ -69,6 +77,7 @@ int main(int argc, char** argv) {
       std::printf("Error loading file\n");
       return -1;
     }
+    if (too_large(data)) return -1;
     bce_gpu_ctx* ctx = nullptr;
     int rc = bce_gpu_open(0, &ctx);
     if (rc) return gpu_failure(ctx, rc);
@@ -93,6 +102,7 @@ int main(int argc, char** argv) {
       std::printf("Error loading file\n");
       return -1;
     }
+    if (too_large(data)) return -1;
     const bool timing = std::getenv("BCE_TIME") != nullptr;
     const auto t_read = clock::now();
     bce_gpu_ctx* ctx = nullptr;
@@ -140,8 +150,10 @@ int main(int argc, char** argv) {
       return -1;
     }
     archive.seekg(0, std::ios::beg);
+    // an archive is a whole number of 16-bit words (bce.cpp:1424-1427): an odd or empty size is a damaged
+    // file (the reference reads `size` bytes into size/2 words and overruns by one, bce.cpp:1441-1445)
     std::vector<uint16_t> words(size_t(size) / sizeof(uint16_t));
-    if (size > 0 && !archive.read(reinterpret_cast<char*>(words.data()), size)) {
+    if (size < 2 || (size & 1) || !archive.read(reinterpret_cast<char*>(words.data()), size)) {
       std::printf("Could not read Archive.\n");
       return -2;
     }

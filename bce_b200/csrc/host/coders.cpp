@@ -50,6 +50,12 @@ bool load_config_file(const std::string& path, ConfigTable& table) {
     std::printf("Could not read Config.\n");
     return false;
   }
+  for (const auto& row : tmp)                                       // context bits are coded in 0..5 (bce.cpp:686): anything
+    for (uint8_t bits : row)                                          // else cannot have come from `bce -s`
+      if (bits > 5) {
+        std::printf("Config holds context bits above 5; ignored.\n");
+        return false;
+      }
   table = tmp;
   return true;
 }

@@ -277,13 +277,16 @@ int decode_archive(std::vector<uint16_t>& archive, bool low_memory, std::vector<
     rc = decode_to_ranks(archive, ranks, n, offset);
   } catch (const std::bad_alloc&) {
     return BCE_GPU_E_NOMEM;
+  } catch (...) {                                                             // e.g. std::system_error from a level worker thread
+    return BCE_GPU_E_INTERNAL;
   }
   if (rc) return rc;
   const auto t1 = clk::now();
   if (timing) std::fprintf(stderr, "[bce] decode loop %.3f s (n = %u)\n", std::chrono::duration<double>(t1 - t0).count(), n);
   std::vector<uint16_t>().swap(archive);                                      // :1203
   if (low_memory) {
-    out = unbwt_serial(ranks, offset, n);
+    try { out = unbwt_serial(ranks, offset, n); }
+    catch (const std::bad_alloc&) { return BCE_GPU_E_NOMEM; }
     return BCE_GPU_OK;
   }
   bce_gpu_ctx* ctx = nullptr;
@@ -291,7 +294,8 @@ int decode_archive(std::vector<uint16_t>& archive, bool low_memory, std::vector<
   if (rc) return rc;
   const uint64_t* lv[8];
   for (int j = 0; j < 8; ++j) lv[j] = ranks[j].words().data();
-  out.resize(n);
+  try { out.resize(n); }
+  catch (const std::bad_alloc&) { bce_gpu_close(ctx); return BCE_GPU_E_NOMEM; }
   const auto t2 = clk::now();
   rc = bce_gpu_unbwt(ctx, lv, offset % n, n, out.data());                     // unbwt::bytewise, :1043-1103
   const auto t3 = clk::now();

@@ -20,6 +20,18 @@ static ConfigTable table_from(const uint8_t* cfg288) {
   return t;
 }
 
+// The C ABI never lets an exception out: allocation failures become BCE_GPU_E_NOMEM.
+#define BCE_HOST_GUARD(body)                                   \
+  try { body }                                                 \
+  catch (const std::bad_alloc&) { return BCE_GPU_E_NOMEM; }    \
+  catch (...) { return BCE_GPU_E_INTERNAL; }
+
+static bool config_ok(const uint8_t* cfg288) {                 // context bits are coded in 0..5 (bce.cpp:686)
+  if (!cfg288) return true;
+  for (int i = 0; i < 288; ++i) if (cfg288[i] > 5) return false;
+  return true;
+}
+
 extern "C" {
 
 const uint8_t* bce_host_default_config(void) {
@@ -28,29 +40,31 @@ const uint8_t* bce_host_default_config(void) {
 void bce_host_free(void* p) { std::free(p); }
 
 bce_archive_writer* bce_archive_begin(uint32_t n, const uint32_t C[8], const uint8_t* cfg288) {
-  if (!C || n == 0) return nullptr;
+  if (!C || n == 0 || n >= 0x80000000u || !config_ok(cfg288)) return nullptr;
   auto* h = new (std::nothrow) bce_archive_writer{nullptr};
   if (!h) return nullptr;
-  h->w = new (std::nothrow) ArchiveWriter(n, C, table_from(cfg288));
+  try { h->w = new ArchiveWriter(n, C, table_from(cfg288)); }
+  catch (...) { h->w = nullptr; }
   if (!h->w) { delete h; return nullptr; }
   return h;
 }
 int bce_archive_feed(bce_archive_writer* h, const bce_cse_batch* batch, int threads) {
   if (!h || !batch) return BCE_GPU_E_ARG;
-  h->w->feed(*batch, threads);
+  BCE_HOST_GUARD(h->w->feed(*batch, threads);)
   return BCE_GPU_OK;
 }
 int bce_archive_feed_words(bce_archive_writer* h, const bce_cse_words* batch, int threads) {
   if (!h || !batch) return BCE_GPU_E_ARG;
-  h->w->feed_words(*batch, threads);
+  BCE_HOST_GUARD(h->w->feed_words(*batch, threads);)
   return BCE_GPU_OK;
 }
 int bce_scan_feed_words(bce_scan* h, const bce_cse_words* batch) {
   if (!h || !batch) return BCE_GPU_E_ARG;
-  h->s->feed_words(*batch);
+  BCE_HOST_GUARD(h->s->feed_words(*batch);)
   return BCE_GPU_OK;
 }
 size_t bce_host_pack_counts(int mode, const uint8_t* cfg288, int stream, const bce_tuple* t, size_t count, uint32_t* words) {
+  if (!config_ok(cfg288) || stream < 0 || stream > 7) return 0;
   ConfigTable tab = table_from(cfg288);
   size_t at = 0;
   for (size_t i = 0; i < count; ++i)
@@ -59,7 +73,9 @@ size_t bce_host_pack_counts(int mode, const uint8_t* cfg288, int stream, const b
 }
 int bce_archive_finish(bce_archive_writer* h, uint32_t offset, uint16_t** words, size_t* nwords) {
   if (!h || !words || !nwords) return BCE_GPU_E_ARG;
-  std::vector<uint16_t> out = h->w->finish(offset);
+  std::vector<uint16_t> out;
+  try { out = h->w->finish(offset); }
+  catch (...) { delete h->w; delete h; return BCE_GPU_E_NOMEM; }
   delete h->w;
   delete h;
   uint16_t* mem = static_cast<uint16_t*>(std::malloc(out.size() * sizeof(uint16_t) + 2));
@@ -78,29 +94,37 @@ void bce_archive_abort(bce_archive_writer* h) {
 bce_scan* bce_scan_begin(void) {
   auto* h = new (std::nothrow) bce_scan{nullptr};
   if (!h) return nullptr;
-  h->s = new (std::nothrow) ScanSession();
+  try { h->s = new ScanSession(); }
+  catch (...) { h->s = nullptr; }
   if (!h->s) { delete h; return nullptr; }
   return h;
 }
 int bce_scan_feed(bce_scan* h, const bce_cse_batch* batch) {
   if (!h || !batch) return BCE_GPU_E_ARG;
-  h->s->feed(*batch);
+  BCE_HOST_GUARD(h->s->feed(*batch);)
   return BCE_GPU_OK;
 }
 int bce_scan_finish(bce_scan* h, uint8_t cfg288_out[288]) {
   if (!h || !cfg288_out) return BCE_GPU_E_ARG;
-  ConfigTable t = h->s->finish();
-  std::memcpy(cfg288_out, t.data(), 288);
+  int rc = BCE_GPU_OK;
+  try {
+    ConfigTable t = h->s->finish();
+    std::memcpy(cfg288_out, t.data(), 288);
+  } catch (const std::bad_alloc&) { rc = BCE_GPU_E_NOMEM; }
+  catch (...) { rc = BCE_GPU_E_INTERNAL; }
   delete h->s;
   delete h;
-  return BCE_GPU_OK;
+  return rc;
 }
 
 int bce_decode_buffer(const uint16_t* words, size_t nwords, int low_memory, uint8_t** out, size_t* nout) {
   if (!words || !out || !nout) return BCE_GPU_E_ARG;
-  std::vector<uint16_t> archive(words, words + nwords);
   std::vector<uint8_t> text;
-  const int rc = decode_archive(archive, low_memory != 0, text);                 // BCE::decode, bce.cpp:1169-1233
+  int rc = BCE_GPU_OK;
+  BCE_HOST_GUARD(
+    std::vector<uint16_t> archive(words, words + nwords);
+    rc = decode_archive(archive, low_memory != 0, text);                         // BCE::decode, bce.cpp:1169-1233
+  )
   if (rc) return rc;
   uint8_t* mem = static_cast<uint8_t*>(std::malloc(text.size() + 1));
   if (!mem) return BCE_GPU_E_NOMEM;

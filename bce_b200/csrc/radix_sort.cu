@@ -22,7 +22,9 @@ namespace bce {
 
 constexpr int RS_MIN_TILE = 2048;       // smallest tile of any kernel configuration (descriptor sizing)
 constexpr int RS_MAX_PASSES = kRadixMaxPasses;
-
+constexpr int kRadixThreads = 256, kRadixItems = 24;                       // tile of the stable and the unordered pass
+constexpr size_t kRadixSmem = size_t(kRadixThreads) * kRadixItems * 12 + size_t(kRadixThreads / 32) * 1024;
+constexpr size_t kRadixUnorderedSmem = size_t(256) * kRadixItems * 12;
 
 size_t radix_desc_words(uint32_t m) { return (size_t(m) / RS_MIN_TILE + 1) * 256; }
 
@@ -273,14 +275,9 @@ __global__ void __launch_bounds__(256, MIN_CTAS) radix_unordered_kernel(RadixPas
   }
 }
 
-}  // namespace bce
-
-#include "radix_chunked.cuh"
-
-namespace bce {
-
-static uint32_t g_radix_dbg = 0;
-static double env_size_d(const char* name, double dflt) { const char* v = getenv(name); return v && *v ? atof(v) : dflt; }
+#ifdef BCE_GPU_EXPERIMENTS
+static uint32_t g_radix_dbg = 0;     // bce_gpu_dbg_radix: 1 = skip the chained scan (timing only, output order wrong)
+#endif
 void byte_hist_launch(Ctx* c, const uint8_t* L, uint32_t n, uint32_t* d_hist);   // wavelet.cu
 
 int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uint32_t* valB,
@@ -325,12 +322,7 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
     for (int p = npass - 1; p >= 0; --p)
       for (int d = 0; d < 256; ++d) h_hist[p * 256 + d] = h_hist[d];
   } else {
-    static bool hist_attr = false;
     const size_t hsmem = size_t(RH_WARPS) * npass * 256 * 4;
-    if (!hist_attr) {
-      BCE_CUDA(c, cudaFuncSetAttribute(radix_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RH_WARPS * RS_MAX_PASSES * 1024));
-      hist_attr = true;
-    }
     uint64_t hb64 = (uint64_t(m) + 255) / 256, hbmax = uint64_t(c->sm_count) * 3;
     int hb = int(hb64 < hbmax ? hb64 : hbmax);
     radix_hist_kernel<<<hb, RH_THREADS, hsmem, c->stream>>>(keyA, m, npass, sh, d_hist);
@@ -357,55 +349,13 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
 
   uint64_t* kin = keyA; uint64_t* kout = keyB;
   uint32_t* vin = valA; uint32_t* vout = valB;
-  // kernel configuration (threads x keys per thread); BCE_GPU_RADIX_CFG picks one for experiments
-  struct Cfg { void (*fn)(RadixPass); int threads, items; void (*fn_ballot)(RadixPass); };
-  static const Cfg cfgs[] = {
-    {radix_onesweep_kernel<256, 12, 3>, 256, 12},
-    {radix_onesweep_kernel<256, 16, 3>, 256, 16},
-    {radix_onesweep_kernel<512, 8, 2>, 512, 8},
-    {radix_onesweep_kernel<384, 12, 2>, 384, 12},
-    {radix_onesweep_kernel<256, 8, 4>, 256, 8},
-    {radix_onesweep_kernel<512, 12, 1>, 512, 12},
-    {radix_onesweep_kernel<256, 20, 3>, 256, 20},
-    {radix_onesweep_kernel<256, 24, 2>, 256, 24, radix_onesweep_kernel<256, 24, 2, true>},
-    {radix_onesweep_kernel<256, 28, 2>, 256, 28},
-    {radix_onesweep_kernel<256, 32, 2>, 256, 32},
-    {radix_onesweep_kernel<384, 16, 2>, 384, 16},
-    {radix_onesweep_kernel<512, 16, 1>, 512, 16},
-  };
-  int which_cfg = 7;          // 256 x 24, 2 CTAs/SM: fastest on B200 on real keys (1 GB text, radix stage: 125 ms; 256 x 16 x 3 CTAs: 140; 256 x 20 x 3: 134; 256 x 28 x 2: 129; 384 x 16 x 2: 149; 512 x 16 x 1: 166)
-  { const char* v = getenv("BCE_GPU_RADIX_CFG"); if (v && *v >= '0' && *v <= '9') which_cfg = *v - '0'; else if (v && *v >= 'a' && *v <= 'b') which_cfg = 10 + *v - 'a'; }
-  const Cfg& cfg = cfgs[which_cfg];
-  const int RS_TILE = cfg.threads * cfg.items;
-  const int RS_THREADS = cfg.threads;
-  const size_t rs_smem = size_t(RS_TILE) * 12 + size_t(cfg.threads / 32) * 1024;
-  static bool attr_set[12] = {};
-  if (!attr_set[which_cfg]) {
-    if (cfg.fn_ballot) BCE_CUDA(c, cudaFuncSetAttribute(cfg.fn_ballot, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem)));
-    BCE_CUDA(c, cudaFuncSetAttribute(cfg.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem)));
-    attr_set[which_cfg] = true;
-  }
+  // 256 threads x 24 keys, 2 CTAs/SM: fastest tile shape on B200 on real keys (1 GB text, radix stage 125 ms; 256 x 16 x 3 CTAs:
+  // 140; 256 x 20 x 3: 134; 256 x 28 x 2: 129; 384 x 16 x 2: 149; 512 x 16 x 1: 166 -- profiles/r1_radix_experiments.md)
+  constexpr int RS_THREADS = kRadixThreads, RS_TILE = kRadixThreads * kRadixItems;
+  constexpr size_t rs_smem = kRadixSmem;
   const uint32_t tiles = (m + RS_TILE - 1) / RS_TILE;
-  // single-pass onesweep kernel (default) or chunked reduce/scan/scatter (BCE_GPU_RADIX=chunked):
-  // measured on B200 the chunked variant is the slower one (100 M random pairs, 8 passes:
-  // 16.1 ms against 9.9 ms), see profiles/r1_radix_experiments.md
-  const char* which = getenv("BCE_GPU_RADIX");
-  const bool chunked = which && which[0] == 'c';
-  uint32_t chunk = 0, chunks = 0;
-  uint32_t* d_chist = nullptr;
-  uint32_t* d_offs = nullptr;
-  if (chunked) {
-    const uint32_t ctas = uint32_t(c->sm_count) * 3;                      // 3 resident CTAs per SM
-    const uint32_t dtiles = (m + RD_TILE - 1) / RD_TILE;
-    const uint32_t per = (dtiles + ctas - 1) / ctas;                      // tiles per chunk
-    chunk = per * RD_TILE;
-    chunks = (m + chunk - 1) / chunk;
-    BCE_TRY(c->radix_tmp.ensure(c, size_t(chunks) * 256 * 4 * 2));
-    d_chist = c->radix_tmp.as<uint32_t>();
-    d_offs = d_chist + size_t(chunks) * 256;
-  }
-  const bool unordered_first = !getenv("BCE_GPU_RADIX_STABLE_FIRST");
-  const double ballot_above = double(env_size_d("BCE_GPU_RADIX_BALLOT_ABOVE", 24.0));
+  const bool unordered_first = exp_env("BCE_GPU_RADIX_STABLE_FIRST", 0) == 0;
+  const double ballot_above = double(exp_env("BCE_GPU_RADIX_BALLOT_ABOVE", 24));
   int ran = 0;
   for (int p = 0; p < npass; ++p) {
     if (!run[p]) continue;
@@ -417,28 +367,18 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
     a.ticket = d_ticket + p;
     a.tag = uint32_t(next_tag(c));
     a.err = d_err;
+#ifdef BCE_GPU_EXPERIMENTS
     a.dbg = g_radix_dbg;
+#else
+    a.dbg = 0;
+#endif
     const bool timed = c->pass_ev_n + 2 <= 256;
     if (timed) cudaEventRecord(c->pass_ev[c->pass_ev_n], c->stream);
-    if (chunked) {
-      RadixDown dn;
-      dn.kin = kin; dn.vin = vin; dn.kout = kout; dn.vout = vout;
-      dn.m = m; dn.chunk = chunk; dn.shift = shifts[p]; dn.offs = d_offs;
-      radix_upsweep_kernel<<<chunks, RD_THREADS, 0, c->stream>>>(kin, m, chunk, shifts[p], d_chist);
-      radix_chunk_scan_kernel<<<1, 256, 0, c->stream>>>(d_chist, chunks, d_offs);
-      radix_downsweep_kernel<<<chunks, RD_THREADS, 0, c->stream>>>(dn);
-      c->stats.gpu_launches += 2;
-    } else if (ran == 0 && unordered_first) {
+    if (ran == 0 && unordered_first) {
       uint32_t* d_cursor = reinterpret_cast<uint32_t*>(small + kSmallRadixCursor);
       BCE_CUDA(c, cudaMemsetAsync(d_cursor, 0, 256 * 4, c->stream));
-      constexpr int UI = 24;
-      const size_t usmem = size_t(256) * UI * 12;
-      static bool uattr = false;
-      if (!uattr) {
-        BCE_CUDA(c, cudaFuncSetAttribute(radix_unordered_kernel<UI, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(usmem)));
-        BCE_CUDA(c, cudaFuncSetAttribute(radix_unordered_kernel<UI, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(usmem)));
-        uattr = true;
-      }
+      constexpr int UI = kRadixItems;
+      constexpr size_t usmem = kRadixUnorderedSmem;
       const uint32_t ugrid = (m + 256 * UI - 1) / (256 * UI);
       if (src && src->keys_from_text) radix_unordered_kernel<UI, 2, true><<<ugrid, 256, usmem, c->stream>>>(a, d_cursor, window_text);
       else radix_unordered_kernel<UI, 2, false><<<ugrid, 256, usmem, c->stream>>>(a, d_cursor, nullptr);
@@ -452,10 +392,9 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
       // keys that are text windows arrive sorted by the bytes that follow: after the first passes a
       // warp's keys share their context and with it, mostly, the digit
       const bool context_sorted = window_text && ran >= 2;
-      const char* force = getenv("BCE_GPU_RADIX_RANK");          // experiments: "match" / "ballot"
-      bool ballot = cfg.fn_ballot && distinct > ballot_above && !context_sorted;
-      if (force && cfg.fn_ballot) ballot = force[0] == 'b';
-      (ballot ? cfg.fn_ballot : cfg.fn)<<<tiles, RS_THREADS, rs_smem, c->stream>>>(a);
+      const bool ballot = distinct > ballot_above && !context_sorted;
+      if (ballot) radix_onesweep_kernel<kRadixThreads, kRadixItems, 2, true><<<tiles, RS_THREADS, rs_smem, c->stream>>>(a);
+      else radix_onesweep_kernel<kRadixThreads, kRadixItems, 2, false><<<tiles, RS_THREADS, rs_smem, c->stream>>>(a);
     }
     if (timed) { cudaEventRecord(c->pass_ev[c->pass_ev_n + 1], c->stream); c->pass_ev_n += 2; }
     c->stats.gpu_launches++;
@@ -473,7 +412,21 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
 }
 
 
-// ---- development aid (not part of include/bce_gpu.h): sort m pseudo-random pairs -----------
+// Function attributes are per device: bce_gpu_open sets them for the context's device.
+int radix_init_device(Ctx* c) {
+  BCE_CUDA(c, cudaFuncSetAttribute(radix_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RH_WARPS * RS_MAX_PASSES * 1024));
+  BCE_CUDA(c, cudaFuncSetAttribute(radix_onesweep_kernel<kRadixThreads, kRadixItems, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRadixSmem)));
+  BCE_CUDA(c, cudaFuncSetAttribute(radix_onesweep_kernel<kRadixThreads, kRadixItems, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRadixSmem)));
+  BCE_CUDA(c, cudaFuncSetAttribute(radix_unordered_kernel<kRadixItems, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRadixUnorderedSmem)));
+  BCE_CUDA(c, cudaFuncSetAttribute(radix_unordered_kernel<kRadixItems, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kRadixUnorderedSmem)));
+  return BCE_GPU_OK;
+}
+
+}  // namespace bce
+
+#ifdef BCE_GPU_EXPERIMENTS
+// ---- development aid (experiment builds only, not part of include/bce_gpu.h): sort m pseudo-random pairs
+namespace bce {
 __global__ void dbg_fill_kernel(uint64_t* k, uint32_t* v, uint32_t m) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
@@ -521,3 +474,4 @@ extern "C" int bce_gpu_dbg_radix(bce_gpu_ctx* h, uint32_t m, int npass, int flag
   if (unsorted_out) *unsorted_out = int(*hb);
   return BCE_GPU_OK;
 }
+#endif  // BCE_GPU_EXPERIMENTS

@@ -447,10 +447,9 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
   S.gpu_launches++;
   // the first radix pass of round 0 makes keys and indices from the text itself (BCE_GPU_PACK=1: a
   // separate pack kernel writes them first)
-  const bool use_local = !getenv("BCE_GPU_NO_LOCAL_SORT");
-  uint32_t local_min = 1u << 20;           // smaller working sets take the plain radix path (BCE_GPU_LOCAL_MIN: tests)
-  if (const char* v = getenv("BCE_GPU_LOCAL_MIN")) local_min = uint32_t(strtoul(v, nullptr, 10));
-  const bool fused_pack = !getenv("BCE_GPU_PACK") && !getenv("BCE_GPU_RADIX_STABLE_FIRST") && !getenv("BCE_GPU_RADIX");
+  const bool use_local = exp_env("BCE_GPU_NO_LOCAL_SORT", 0) == 0;
+  const uint32_t local_min = c->local_sort_min;   // smaller working sets take the plain radix path (BCE_GPU_OPT_LOCAL_SORT_MIN)
+  const bool fused_pack = exp_env("BCE_GPU_PACK", 0) == 0 && exp_env("BCE_GPU_RADIX_STABLE_FIRST", 0) == 0;
   if (!fused_pack) {
     pack_keys_kernel<<<(n + 256 * PK_ROWS - 1) / (256 * PK_ROWS), 256, 0, st>>>(T, n, keyA, idxA);
     S.gpu_launches++;
@@ -473,7 +472,7 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     bool tiebreak = false;
     // Large working sets update the rank array through pairs partitioned by the top 8 bits of idx
     // (see the re-rank step below); decided here because the key rebuild counts that digit too.
-    const bool partitioned = !getenv("BCE_GPU_NO_PARTITION") && m >= (8u << 20) && size_t(n) * 4 > (size_t(64) << 20);
+    const bool partitioned = exp_env("BCE_GPU_NO_PARTITION", 0) == 0 && m >= (8u << 20) && size_t(n) * 4 > (size_t(64) << 20);
     const int pshift = 32 + std::max(0, nbits - 8);
     bool local_plan = false;               // this round's sort is done tile by tile (local_sort.cuh)
     uint32_t m_fb = 0;                     // ... except for this many slots, which go through the radix sort
@@ -580,7 +579,7 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     a.pairs = partitioned ? pair_buf : nullptr;
     // the pairs leave the kernel already binned by the top bits of idx (BCE_GPU_PARTITION=radix: in slot
     // order, binned afterwards by one keys-only radix pass)
-    const bool binned = partitioned && !getenv("BCE_GPU_PARTITION");
+    const bool binned = partitioned && exp_env("BCE_GPU_PARTITION", 0) == 0;
     a.part_cursor = nullptr;
     a.part_shift = pshift - 32;
     if (binned) {
@@ -605,7 +604,7 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     a.ticket = d_ticket;
     a.tag = uint32_t(next_tag(c));
     a.err = d_err;
-    { const char* v = getenv("BCE_GPU_RERANK_DBG"); a.dbg = v ? uint32_t(atoi(v)) : 0u; }
+    a.dbg = uint32_t(exp_env("BCE_GPU_RERANK_DBG", 0));      // experiment builds only: timing with parts switched off
     BCE_CUDA(c, cudaMemsetAsync(d_ticket, 0, 4, st));
     rerank_kernel<<<a.tiles, RR_THREADS, 0, st>>>(a);
     S.gpu_launches++;

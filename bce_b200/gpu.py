@@ -26,8 +26,9 @@ ABI_SYMBOLS = [
     "bce_gpu_last_error", "bce_gpu_get_stats", "bce_gpu_set_scratch_limit", "bce_gpu_bwt",
     "bce_gpu_wavelet", "bce_gpu_cse_begin", "bce_gpu_cse_next", "bce_gpu_compress_front",
     "bce_gpu_stage_input", "bce_gpu_front_resident", "bce_gpu_unbwt",
-    "bce_gpu_set_emit_mode", "bce_gpu_cse_next_words",
+    "bce_gpu_set_emit_mode", "bce_gpu_cse_next_words", "bce_gpu_set_option",
 ]
+OPT_EMIT_BATCH_BYTES, OPT_LOCAL_SORT_MIN = 1, 2
 
 
 class BceGpuError(RuntimeError):
@@ -100,6 +101,7 @@ def load_library() -> C.CDLL:
     lib.bce_gpu_last_error.restype = C.c_char_p
     lib.bce_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.bce_gpu_set_scratch_limit.argtypes = [vp, C.c_size_t]
+    lib.bce_gpu_set_option.argtypes = [vp, C.c_int, C.c_uint64]
     lib.bce_gpu_bwt.argtypes = [vp, vp, u32, vp, u32p, vp]
     lib.bce_gpu_wavelet.argtypes = [vp, vp, u32, C.POINTER(vp), u32p]
     lib.bce_gpu_cse_begin.argtypes = [vp, vp, u32, u32p]
@@ -195,6 +197,7 @@ class Frontend:
             if batch.done:
                 break
         out = [np.concatenate(s) if s else np.zeros((0, 5), dtype=np.uint32) for s in streams]
+        self.last_batches = batches
         return out, batches
 
     def cse(self, L=None, n: int | None = None):
@@ -288,3 +291,7 @@ class Frontend:
 
     def set_scratch_limit(self, nbytes: int):
         self._check(self.lib.bce_gpu_set_scratch_limit(self.h, nbytes))
+
+    def set_option(self, option: int, value: int):
+        """bce_gpu_set_option: OPT_EMIT_BATCH_BYTES / OPT_LOCAL_SORT_MIN (0 = default)."""
+        self._check(self.lib.bce_gpu_set_option(self.h, option, value))

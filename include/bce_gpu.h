@@ -96,6 +96,13 @@ const char *bce_gpu_last_error(const bce_gpu_ctx *ctx);
 int bce_gpu_get_stats(const bce_gpu_ctx *ctx, bce_gpu_stats *out);
 /* cap on the scratch arena in bytes (0 = default: a share of free device memory) */
 int bce_gpu_set_scratch_limit(bce_gpu_ctx *ctx, size_t bytes);
+/* Tuning options of a context (value 0 = back to the default).  Results never depend on them.
+ *   EMIT_BATCH_BYTES  target size of one batch of emitted counts handed back by cse_next* (default
+ *                     1 GiB; small values force many batches -- used by the tests of the draining path)
+ *   LOCAL_SORT_MIN    working sets of the suffix sort below this many rotations take the plain
+ *                     radix path instead of the tile-local sort (default 2^20) */
+enum { BCE_GPU_OPT_EMIT_BATCH_BYTES = 1, BCE_GPU_OPT_LOCAL_SORT_MIN = 2 };
+int bce_gpu_set_option(bce_gpu_ctx *ctx, int option, uint64_t value);
 
 /* ---- stage A: suffix sort / BWT ------------------------------------------------
  * Replaces File::rotate (bce.cpp:858-894) and File::bwt with its divbwt call into

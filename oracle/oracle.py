@@ -187,6 +187,8 @@ def tap():
         t.bce_ref_seconds_encode.restype = C.c_double
         t.bce_ref_calls.argtypes = [C.c_int]
         t.bce_ref_calls.restype = C.c_uint64
+        t.bce_ref_checksum.argtypes = [C.c_int, C.c_int]
+        t.bce_ref_checksum.restype = C.c_uint64
         t.bce_ref_adaptive.argtypes = [C.c_int, C.POINTER(C.c_size_t)]
         t.bce_ref_adaptive.restype = C.c_void_p
         t.bce_ref_uniform.argtypes = [C.c_int, C.POINTER(C.c_size_t)]
@@ -194,14 +196,30 @@ def tap():
     return _tap
 
 
-def ref_front(data, want_bwt=True, want_ranks=False, record=True):
+A64 = 0x9E3779B97F4A7C15
+
+
+def call_checksum(tuples, first_index: int = 0):
+    """(sum, wsum) of ref_tap.cpp's per-stream call checksum over an (E, 5) uint32 array whose
+    first row is call number `first_index` of its stream; both mod 2^64, so batches add up."""
+    t = np.ascontiguousarray(tuples, dtype=np.uint32).reshape(-1, 5).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        A = np.uint64(A64)
+        h = t[:, 0]
+        for c in range(1, 5):
+            h = h * A + t[:, c]
+        j = np.arange(first_index, first_index + t.shape[0], dtype=np.uint64)
+        return int(h.sum(dtype=np.uint64)), int((h * (j * np.uint64(2) + np.uint64(1))).sum(dtype=np.uint64))
+
+
+def ref_front(data, want_bwt=True, want_ranks=False, record=True, checksum=False):
     """Run the unmodified reference front end (RankFile + BCE<tap>::encode) on `data`."""
     T = _u8(data)
     with tempfile.NamedTemporaryFile(suffix=".in", delete=False) as f:
         f.write(T.tobytes())
         path = f.name
     try:
-        flags = (1 if want_bwt else 0) | (2 if want_ranks else 0) | (0 if record else 4)
+        flags = (1 if want_bwt else 0) | (2 if want_ranks else 0) | (0 if record else 4) | (8 if checksum else 0)
         # the reference prints progress to stdout; keep pytest output clean
         devnull = os.open(os.devnull, os.O_WRONLY)
         saved = os.dup(1)
@@ -228,19 +246,24 @@ def ref_front(data, want_bwt=True, want_ranks=False, record=True):
         words = n // 32 + 1
         out["ranks"] = [np.ctypeslib.as_array((C.c_uint64 * words).from_address(t.bce_ref_ranks(j))).copy()
                         for j in range(8)]
+    if record or checksum:
+        out["checksum"] = [(int(t.bce_ref_checksum(i, 0)), int(t.bce_ref_checksum(i, 1))) for i in range(8)]
+    Cv = []
+    for i in range(8):
+        cnt = C.c_size_t()
+        p = t.bce_ref_uniform(i, C.byref(cnt))
+        u = np.ctypeslib.as_array((C.c_uint32 * (cnt.value * 2)).from_address(p)).reshape(-1, 2)
+        Cv.append(int(u[0, 0]))        # first uniform call on stream i is set(C[i], n+1), bce.cpp:1129
+    out["C"] = Cv
     if record:
-        streams, Cv = [], []
+        streams = []
         for i in range(8):
             cnt = C.c_size_t()
             p = t.bce_ref_adaptive(i, C.byref(cnt))
             a = (np.ctypeslib.as_array((C.c_uint32 * (cnt.value * 5)).from_address(p)).reshape(-1, 5).copy()
                  if cnt.value else np.zeros((0, 5), dtype=np.uint32))
             streams.append(a)
-            p = t.bce_ref_uniform(i, C.byref(cnt))
-            u = np.ctypeslib.as_array((C.c_uint32 * (cnt.value * 2)).from_address(p)).reshape(-1, 2)
-            Cv.append(int(u[0, 0]))        # first uniform call on stream i is set(C[i], n+1), bce.cpp:1129
         out["streams"] = streams
-        out["C"] = Cv
     return out
 
 

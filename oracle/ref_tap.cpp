@@ -23,12 +23,19 @@ namespace {
 struct TapStore {
   std::vector<uint32_t> adaptive[9];   /* 5 words per call of set(s,k,c1,c2,cs) */
   std::vector<uint32_t> uniform[9];    /* 2 words per call of set(s,k)          */
-  bool record = true;
+  bool record = true, checksum = true;
   uint64_t calls[9] = {0};
+  /* order-sensitive checksum of the adaptive calls of a stream, kept when asked for (flag 8) so that
+   * inputs too large to record (1 GB: 44 GB of tuples) are still pinned call by call:
+   *   h_j = ((((s*A + k)*A + c1)*A + c2)*A + cs)  mod 2^64,  A = 0x9E3779B97F4A7C15
+   *   sum = SUM_j h_j,   wsum = SUM_j h_j * (2 j + 1)       (j = 0-based call index)      */
+  uint64_t sum[9] = {0}, wsum[9] = {0};
   void reset() {
     for (auto& v : adaptive) std::vector<uint32_t>().swap(v);
     for (auto& v : uniform) std::vector<uint32_t>().swap(v);
     std::memset(calls, 0, sizeof calls);
+    std::memset(sum, 0, sizeof sum);
+    std::memset(wsum, 0, sizeof wsum);
   }
 };
 TapStore g_tap;
@@ -43,13 +50,18 @@ class TapCoder : public VCoder<TapCoder> {
   explicit TapCoder(int i, value_type&&) : id_(i < 0 || i > 7 ? 8 : i) {}
 
   void set(uint32_t s, uint32_t k, uint32_t c1, uint32_t c2, uint32_t cs) {
+    if (g_tap.checksum) {
+      const uint64_t A = 0x9E3779B97F4A7C15ull;
+      uint64_t h = ((((uint64_t(s) * A + k) * A + c1) * A + c2) * A + cs);
+      g_tap.sum[id_] += h;
+      g_tap.wsum[id_] += h * (2 * g_tap.calls[id_] + 1);
+    }
     g_tap.calls[id_]++;
     if (!g_tap.record) return;
     auto& v = g_tap.adaptive[id_];
     v.push_back(s); v.push_back(k); v.push_back(c1); v.push_back(c2); v.push_back(cs);
   }
-  void set(uint32_t s, uint32_t k) {
-    if (!g_tap.record) return;
+  void set(uint32_t s, uint32_t k) {   /* a handful of calls per run (roots, header): always kept */
     auto& v = g_tap.uniform[id_];
     v.push_back(s); v.push_back(k);
   }
@@ -84,10 +96,12 @@ extern "C" {
 
 /* Run the reference front end on a file.  flags: 1 = also keep the BWT bytes,
  * 2 = also keep the 8 rank arrays (rebuilt through Rank's public get/bit),
- * 4 = do not record tuples (timing runs: only count them). Returns 0 / -1. */
+ * 4 = do not record tuples (timing runs: only count them), 8 = keep the per-stream call
+ * checksums (always on when recording). Returns 0 / -1. */
 int bce_ref_front(const char* path, int flags) {
   g_tap.reset();
   g_tap.record = !(flags & 4);
+  g_tap.checksum = g_tap.record || (flags & 8);
   g_bwt.clear();
   for (auto& r : g_ranks) r.clear();
 
@@ -133,6 +147,7 @@ const uint64_t* bce_ref_ranks(int level) { return g_ranks[level].data(); }
 double bce_ref_seconds_rankfile(void) { return g_t_front; }   /* rotate + BWT + wavelet */
 double bce_ref_seconds_encode(void) { return g_t_encode; }    /* CSE loop with the tap coder */
 uint64_t bce_ref_calls(int stream) { return g_tap.calls[stream]; }
+uint64_t bce_ref_checksum(int stream, int weighted) { return weighted ? g_tap.wsum[stream] : g_tap.sum[stream]; }
 
 /* stream 0..7 = wavelet levels, 8 = header coder */
 const uint32_t* bce_ref_adaptive(int stream, size_t* calls) {

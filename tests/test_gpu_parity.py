@@ -83,14 +83,20 @@ def test_unbwt(frontend, name, data, primitive):
         assert first_diff(out, oracle.unbwt_bitwise(ranks, off, len(data))) is None
 
 
-def test_small_emission_buffers_force_draining(frontend, monkeypatch):
+def test_small_emission_buffers_force_draining(frontend):
     """Several cse_next batches must concatenate to the same streams."""
     from bce_b200 import synth
     data = synth.generate("markov2-text", 400_000, 3).tobytes()
     Lo, _, _ = oracle.bwt(data)
     want = oracle.cse(oracle.wavelet(Lo), len(data))
-    monkeypatch.setenv("BCE_GPU_PINNED_LIMIT", str(8 * 20 * 210_000))
-    Cv, streams = frontend.cse(Lo)
+    from bce_b200.gpu import OPT_EMIT_BATCH_BYTES
+    frontend.set_option(OPT_EMIT_BATCH_BYTES, 8 * 20 * 210_000)
+    try:
+        Cv, streams = frontend.cse(Lo)
+        batches = frontend.last_batches
+    finally:
+        frontend.set_option(OPT_EMIT_BATCH_BYTES, 0)
+    assert batches > 1, "the option did not force several batches"
     for i in range(8):
         assert first_diff(streams[i], want["streams"][i]) is None, i
 
@@ -161,20 +167,25 @@ def test_random_small_inputs_archive_parity(frontend):
         assert got == oracle.compress(data), (trial, n, sigma)
 
 
-def test_tile_local_sort_forced_on_small_inputs(frontend, monkeypatch):
+def test_tile_local_sort_forced_on_small_inputs(frontend):
     """Rounds >= 1 of the suffix sort normally go tile by tile (csrc/local_sort.cuh) only for working sets
     of 2^20 rotations and more, i.e. never on the inputs the oracle can check.  Forced on everything here:
     groups crossing tile boundaries (fall-back radix sort + placement), whole-tile groups (bail-out to the
     radix path), partial last tiles, the index tie-break round of exact powers."""
-    monkeypatch.setenv("BCE_GPU_LOCAL_MIN", "1")
-    for name, data, _ in small_cases() + medium_cases():
-        n = len(data)
-        if n < 2:
-            continue
-        Lo, offo, sao = oracle.bwt(data, want_sa=True)
-        L, off, sa = frontend.bwt(data, want_sa=True)
-        assert off == offo, name
-        assert np.array_equal(np.asarray(sa), np.asarray(sao)), name
-        assert bytes(L) == bytes(Lo), name
-    st = frontend.stats()
-    assert "sort_local_elems" in st
+    from bce_b200.gpu import OPT_LOCAL_SORT_MIN
+    frontend.set_option(OPT_LOCAL_SORT_MIN, 1)
+    local = 0
+    try:
+        for name, data, _ in small_cases() + medium_cases():
+            n = len(data)
+            if n < 2:
+                continue
+            Lo, offo, sao = oracle.bwt(data, want_sa=True)
+            L, off, sa = frontend.bwt(data, want_sa=True)
+            assert off == offo, name
+            assert np.array_equal(np.asarray(sa), np.asarray(sao)), name
+            assert bytes(L) == bytes(Lo), name
+            local += frontend.stats()["sort_local_elems"]
+    finally:
+        frontend.set_option(OPT_LOCAL_SORT_MIN, 0)
+    assert local > 0, "the option did not force the tile-local sort"

@@ -301,6 +301,9 @@ int bce_gpu_set_option(bce_gpu_ctx* h, int option, uint64_t value) {
     case BCE_GPU_OPT_LOCAL_SORT_MIN:
       c->local_sort_min = value ? uint32_t(value > 0xFFFFFFFFull ? 0xFFFFFFFFull : value) : 1u << 20;
       return BCE_GPU_OK;
+    case BCE_GPU_OPT_RESIDENT_CHECKSUM:
+      c->resident_checksum = value != 0;
+      return BCE_GPU_OK;
     default:
       set_error(c, "bce_gpu_set_option: unknown option %d", option);
       return BCE_GPU_E_ARG;
@@ -483,6 +486,20 @@ int bce_gpu_front_resident(bce_gpu_ctx* h, uint32_t* offset_out, uint64_t* tuple
   c->stats.ms_total = c->stats.ms_bwt_total + c->stats.ms_cse_total;
   if (offset_out) *offset_out = c->offset;
   if (tuples_out) *tuples_out = c->emit_mode == BCE_EMIT_RAW ? c->stats.cse_tuples : c->stats.cse_words;
+  return BCE_GPU_OK;
+}
+
+int bce_gpu_resident_checksum(bce_gpu_ctx* h, uint64_t sum[8], uint64_t wsum[8]) {
+  if (!h || !sum || !wsum) return BCE_GPU_E_ARG;
+  Ctx* c = static_cast<Ctx*>(h);
+  bce::begin_call(c);
+  if (!c->cse_resident || !c->cse_done || !c->resident_checksum) {
+    bce::set_error(c, "resident_checksum: no finished front_resident run with BCE_GPU_OPT_RESIDENT_CHECKSUM set");
+    return BCE_GPU_E_STATE;
+  }
+  uint64_t acc[16];
+  BCE_TRY(bce::d2h(c, acc, c->small.as<char>() + bce::kSmallChecksum, sizeof acc));
+  for (int i = 0; i < 8; ++i) { sum[i] = acc[2 * i]; wsum[i] = acc[2 * i + 1]; }
   return BCE_GPU_OK;
 }
 

@@ -185,6 +185,24 @@ __global__ void cse_reset_emitted_kernel(CseDeviceState* S) {
   if (threadIdx.x == 0 && S->status == kCseDrain) S->status = kCseRunning;
 }
 
+// Order-sensitive checksum of a run of emitted words (bce_gpu_resident_checksum): acc[0] += SUM w,
+// acc[1] += SUM w * (2 (first + j) + 1), mod 2^64 -- sums commute, so the atomics do not make it nondeterministic.
+__global__ void __launch_bounds__(256) cse_checksum_kernel(const uint32_t* __restrict__ words, unsigned long long count,
+                                                           unsigned long long first, unsigned long long* acc) {
+  unsigned long long s = 0, ws = 0;
+  for (unsigned long long j = blockIdx.x * 256ull + threadIdx.x; j < count; j += gridDim.x * 256ull) {
+    const unsigned long long w = words[j];
+    s += w;
+    ws += w * (2ull * (first + j) + 1ull);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+    ws += __shfl_xor_sync(0xffffffffu, ws, d);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], s); atomicAdd(&acc[1], ws); }
+}
+
 // vector load of ITEMS consecutive frontier entries; `rev` = stored back to front
 template <int ITEMS>
 __device__ __forceinline__ void load_items(const uint32_t* base, uint32_t first, bool rev, uint32_t cap, uint32_t (&out)[ITEMS]) {
@@ -583,6 +601,7 @@ struct CseHost {
   bool tail_cut = false;                 // hosted emission: the batch was already cut where the frontier collapsed
   bool finished = false;                 // the level loop terminated
   uint32_t desc_epoch = 0;               // round >> 29 at which the descriptors were last cleared
+  unsigned long long sum_words[8] = {};  // resident checksum: words of every stream summed so far
 };
 
 static size_t env_size(const char* name, size_t dflt) { return exp_env(name, dflt); }   // experiment builds only
@@ -679,6 +698,10 @@ int cse_begin(Ctx* c, uint32_t n) {
 
   BCE_CUDA(c, cudaMemsetAsync(a.desc, 0, 3 * desc_tiles * sizeof(uint64_t), st));
   H->desc_epoch = 0;
+  if (c->cse_resident && c->resident_checksum) {
+    BCE_CUDA(c, cudaMemsetAsync(c->small.as<char>() + kSmallChecksum, 0, 16 * sizeof(unsigned long long), st));
+    for (auto& w : H->sum_words) w = 0;
+  }
   cse_init_kernel<<<1, 32, 0, st>>>(a, n);
   c->stats.gpu_launches++;
   BCE_CUDA(c, cudaGetLastError());
@@ -867,6 +890,17 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
   c->stats.cse_visits = h_state->visits;
   c->stats.cse_rounds = h_state->round ? h_state->round : 1;   // the reference's do..while runs at least once
   c->stats.cse_peak_frontier = h_state->peak_frontier;
+  if (c->cse_resident && c->resident_checksum) {
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(c->small.as<char>() + kSmallChecksum);
+    for (int l = 0; l < 8; ++l) {
+      if (!cnt[l]) continue;
+      const int grid = int(std::min<size_t>((cnt[l] + 255) / 256, size_t(c->sm_count) * 8));
+      cse_checksum_kernel<<<grid, 256, 0, st>>>(H->emit_dev[set][l], cnt[l], H->sum_words[l], acc + 2 * l);
+      c->stats.gpu_launches++;
+      H->sum_words[l] += cnt[l];
+    }
+    BCE_CUDA(c, cudaGetLastError());
+  }
   *done = h_state->status == kCseDone;
   if (*done) {
     H->finished = true;

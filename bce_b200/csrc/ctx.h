@@ -55,6 +55,7 @@ struct Ctx : bce_gpu_ctx {
   // options (bce_gpu_set_option)
   size_t emit_batch_bytes = size_t(1) << 30;   // BCE_GPU_OPT_EMIT_BATCH_BYTES
   uint32_t local_sort_min = 1u << 20;          // BCE_GPU_OPT_LOCAL_SORT_MIN
+  bool resident_checksum = false;              // BCE_GPU_OPT_RESIDENT_CHECKSUM
 
   // state of the current input
   uint32_t n = 0;
@@ -88,6 +89,7 @@ constexpr size_t kSmallRerankTotals = kSmallRerankTicket + 64;  // 2 u32
 constexpr size_t kSmallWavelet = kSmallRerankTotals + 64;     // 256 u32 hist + 8 u32 zeros + 8 tickets
 constexpr size_t kSmallCse = kSmallWavelet + 2048;            // CseDeviceState
 constexpr size_t kSmallUnbwt = kSmallCse + 1024;              // inverse-BWT counters
+constexpr size_t kSmallChecksum = 44 * 1024;                  // 8 x 2 u64    per-stream checksums of the resident emission
 constexpr size_t kSmallRadixCursor = 52 * 1024;               // 256 u32      write cursors of a sort's first (unordered) pass
 constexpr size_t kSmallPartHist = 48 * 1024;                  // 256 u32      histogram of the rank-scatter partition digit
 constexpr size_t kSmallBytes = 64 * 1024;

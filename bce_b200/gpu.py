@@ -27,8 +27,9 @@ ABI_SYMBOLS = [
     "bce_gpu_wavelet", "bce_gpu_cse_begin", "bce_gpu_cse_next", "bce_gpu_compress_front",
     "bce_gpu_stage_input", "bce_gpu_front_resident", "bce_gpu_unbwt",
     "bce_gpu_set_emit_mode", "bce_gpu_cse_next_words", "bce_gpu_set_option",
+    "bce_gpu_resident_checksum",
 ]
-OPT_EMIT_BATCH_BYTES, OPT_LOCAL_SORT_MIN = 1, 2
+OPT_EMIT_BATCH_BYTES, OPT_LOCAL_SORT_MIN, OPT_RESIDENT_CHECKSUM = 1, 2, 3
 
 
 class BceGpuError(RuntimeError):
@@ -102,6 +103,7 @@ def load_library() -> C.CDLL:
     lib.bce_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.bce_gpu_set_scratch_limit.argtypes = [vp, C.c_size_t]
     lib.bce_gpu_set_option.argtypes = [vp, C.c_int, C.c_uint64]
+    lib.bce_gpu_resident_checksum.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.bce_gpu_bwt.argtypes = [vp, vp, u32, vp, u32p, vp]
     lib.bce_gpu_wavelet.argtypes = [vp, vp, u32, C.POINTER(vp), u32p]
     lib.bce_gpu_cse_begin.argtypes = [vp, vp, u32, u32p]
@@ -248,6 +250,34 @@ class Frontend:
         out = [np.concatenate(s) if s else np.zeros(0, dtype=np.uint32) for s in streams]
         return int(off.value), [int(x) for x in Cv], out
 
+    def iter_front_batches(self, data, mode: int = EMIT_RAW, cfg: bytes | None = None):
+        """Fused front end, batch by batch, without keeping anything: yields ("head", offset, C[8]) first,
+        then ("batch", [8 uint32 views into the context's pinned buffers]) until the loop is done.  A view
+        is valid until the next batch is asked for (inputs whose counts do not fit in host memory)."""
+        T = _as_u8(data)
+        self.set_emit_mode(mode, cfg)
+        try:
+            off = C.c_uint32()
+            Cv = (C.c_uint32 * 8)()
+            self._check(self.lib.bce_gpu_compress_front(self.h, T.ctypes.data, T.size, C.byref(off), Cv))
+            yield "head", int(off.value), [int(x) for x in Cv]
+            batch = CseWords()
+            while True:
+                self._check(self.lib.bce_gpu_cse_next_words(self.h, C.byref(batch)))
+                views = []
+                for i in range(8):
+                    cnt = int(batch.count[i])
+                    if cnt:
+                        addr = C.addressof(batch.words[i].contents)
+                        views.append(np.ctypeslib.as_array((C.c_uint32 * cnt).from_address(addr)))
+                    else:
+                        views.append(np.zeros(0, dtype=np.uint32))
+                yield "batch", views
+                if batch.done:
+                    break
+        finally:
+            self.set_emit_mode(EMIT_RAW)
+
     def compress_front_discard(self, data):
         """Same call sequence a consumer makes (fused front end, then batches until done) in the
         context's current emission mode; the batches are left in pinned memory (bench e2e leg).
@@ -291,6 +321,12 @@ class Frontend:
 
     def set_scratch_limit(self, nbytes: int):
         self._check(self.lib.bce_gpu_set_scratch_limit(self.h, nbytes))
+
+    def resident_checksum(self):
+        """Per-stream (sum, wsum) of the words the last front_resident run emitted (OPT_RESIDENT_CHECKSUM)."""
+        a, b = (C.c_uint64 * 8)(), (C.c_uint64 * 8)()
+        self._check(self.lib.bce_gpu_resident_checksum(self.h, a, b))
+        return [(int(a[i]), int(b[i])) for i in range(8)]
 
     def set_option(self, option: int, value: int):
         """bce_gpu_set_option: OPT_EMIT_BATCH_BYTES / OPT_LOCAL_SORT_MIN (0 = default)."""

@@ -100,8 +100,9 @@ int bce_gpu_set_scratch_limit(bce_gpu_ctx *ctx, size_t bytes);
  *   EMIT_BATCH_BYTES  target size of one batch of emitted counts handed back by cse_next* (default
  *                     1 GiB; small values force many batches -- used by the tests of the draining path)
  *   LOCAL_SORT_MIN    working sets of the suffix sort below this many rotations take the plain
- *                     radix path instead of the tile-local sort (default 2^20) */
-enum { BCE_GPU_OPT_EMIT_BATCH_BYTES = 1, BCE_GPU_OPT_LOCAL_SORT_MIN = 2 };
+ *                     radix path instead of the tile-local sort (default 2^20)
+ *   RESIDENT_CHECKSUM 1 = front_resident also sums the words it emits (see bce_gpu_resident_checksum) */
+enum { BCE_GPU_OPT_EMIT_BATCH_BYTES = 1, BCE_GPU_OPT_LOCAL_SORT_MIN = 2, BCE_GPU_OPT_RESIDENT_CHECKSUM = 3 };
 int bce_gpu_set_option(bce_gpu_ctx *ctx, int option, uint64_t value);
 
 /* ---- stage A: suffix sort / BWT ------------------------------------------------
@@ -164,6 +165,11 @@ int bce_gpu_compress_front(bce_gpu_ctx *ctx, const uint8_t *T, uint32_t n,
  * of emitted counts.  Used for the `value` leg of bench.py. */
 int bce_gpu_stage_input(bce_gpu_ctx *ctx, const uint8_t *T, uint32_t n);
 int bce_gpu_front_resident(bce_gpu_ctx *ctx, uint32_t *offset_out, uint64_t *tuples_out);
+/* Proof that the resident run emitted what the hosted run hands back: per stream i, over the words
+ * w_0, w_1, ... in emission order (the words bce_gpu_cse_next* would have returned for the mode set with
+ * bce_gpu_set_emit_mode),  sum[i] = SUM w_j  and  wsum[i] = SUM w_j * (2 j + 1),  both mod 2^64.
+ * Needs BCE_GPU_OPT_RESIDENT_CHECKSUM = 1 before front_resident (one extra read of the emitted words). */
+int bce_gpu_resident_checksum(bce_gpu_ctx *ctx, uint64_t sum[8], uint64_t wsum[8]);
 
 /* ---- inverse --------------------------------------------------------------------
  * Replaces unbwt::bytewise::unbwt (bce.cpp:1043-1103): wavelet -> bytes (:1050-1085),

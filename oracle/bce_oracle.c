@@ -510,3 +510,26 @@ int bceo_unbwt_bytewise(const uint64_t *const ranks[8], uint32_t offset, uint32_
   free(L);
   return 0;
 }
+
+/* see bce_oracle.h: the per-stream sums of oracle/ref_tap.cpp (TapStore) over a batch of calls */
+void bceo_call_checksum(const uint32_t *t, size_t count, uint64_t first, uint64_t out[2]) {
+  const uint64_t A = 0x9E3779B97F4A7C15ull;
+  uint64_t sum = 0, wsum = 0;
+  for (size_t j = 0; j < count; ++j, t += 5) {
+    const uint64_t h = ((((uint64_t)t[0] * A + t[1]) * A + t[2]) * A + t[3]) * A + t[4];
+    sum += h;
+    wsum += h * (2 * (first + j) + 1);
+  }
+  out[0] = sum;
+  out[1] = wsum;
+}
+
+void bceo_word_checksum(const uint32_t *w, size_t count, uint64_t first, uint64_t out[2]) {
+  uint64_t sum = 0, wsum = 0;
+  for (size_t j = 0; j < count; ++j) {
+    sum += w[j];
+    wsum += (uint64_t)w[j] * (2 * (first + j) + 1);
+  }
+  out[0] = sum;
+  out[1] = wsum;
+}

@@ -78,6 +78,14 @@ void bceo_wavelet_to_bytes(const uint64_t *const ranks[8], uint32_t n, uint8_t *
 /* the default 9x32 config table, bce.cpp:713-724 */
 const uint8_t *bceo_default_config(void);
 
+/* Checksums used to pin streams too large to store (tests/golden/big_vectors.json):
+ *   calls  (count x 5 words s,k,c1,c2,cs): h_j = ((((s*A + k)*A + c1)*A + c2)*A + cs), A = 0x9E3779B97F4A7C15
+ *   words  (count packed words):           h_j = w_j
+ * out[0] = SUM h_j, out[1] = SUM h_j * (2 (first + j) + 1), mod 2^64 -- the same sums oracle/ref_tap.cpp keeps
+ * per stream of the unmodified reference and bce_gpu_resident_checksum returns for the device. */
+void bceo_call_checksum(const uint32_t *tuples, size_t count, uint64_t first, uint64_t out[2]);
+void bceo_word_checksum(const uint32_t *words, size_t count, uint64_t first, uint64_t out[2]);
+
 void bceo_free(void *p);
 
 #ifdef __cplusplus

@@ -55,6 +55,8 @@ def lib():
         L.bceo_wavelet_to_bytes.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]
         L.bceo_default_config.restype = C.c_void_p
         L.bceo_free.argtypes = [C.c_void_p]
+        L.bceo_call_checksum.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.bceo_word_checksum.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_uint64)]
     return _lib
 
 
@@ -210,6 +212,22 @@ def call_checksum(tuples, first_index: int = 0):
             h = h * A + t[:, c]
         j = np.arange(first_index, first_index + t.shape[0], dtype=np.uint64)
         return int(h.sum(dtype=np.uint64)), int((h * (j * np.uint64(2) + np.uint64(1))).sum(dtype=np.uint64))
+
+
+def call_checksum_fast(tuples, first_index: int = 0):
+    """call_checksum through liboracle (C loop; the GIL is released, so streams can be summed in threads)."""
+    t = np.ascontiguousarray(tuples, dtype=np.uint32)
+    out = (C.c_uint64 * 2)()
+    lib().bceo_call_checksum(t.ctypes.data, t.size // 5, first_index, out)
+    return int(out[0]), int(out[1])
+
+
+def word_checksum(words, first_index: int = 0):
+    """(sum, wsum) of packed words as bce_gpu_resident_checksum defines them."""
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    out = (C.c_uint64 * 2)()
+    lib().bceo_word_checksum(w.ctypes.data, w.size, first_index, out)
+    return int(out[0]), int(out[1])
 
 
 def ref_front(data, want_bwt=True, want_ranks=False, record=True, checksum=False):

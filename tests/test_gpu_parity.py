@@ -102,12 +102,30 @@ def test_small_emission_buffers_force_draining(frontend):
 
 
 def test_resident_matches_hosted(frontend):
+    """The device-resident run (bench.py's `value` leg) emits, word for word and in order, what the hosted run
+    hands back -- in every emission mode."""
     from bce_b200 import synth
+    from bce_b200.gpu import EMIT_CODER, EMIT_RAW, EMIT_SCAN, OPT_RESIDENT_CHECKSUM
     data = synth.generate("enwik-shaped", 500_000, 5).tobytes()
     off, Cv, streams = frontend.compress_front(data)
-    frontend.stage_input(data)
-    off2, tuples = frontend.front_resident()
-    assert off2 == off and tuples == sum(s.shape[0] for s in streams)
+    frontend.set_option(OPT_RESIDENT_CHECKSUM, 1)
+    try:
+        for mode in (EMIT_RAW, EMIT_CODER, EMIT_SCAN):
+            if mode == EMIT_RAW:
+                hosted = [s.reshape(-1) for s in streams]
+            else:
+                _, _, hosted = frontend.compress_front_words(data, mode)
+            frontend.set_emit_mode(mode)
+            frontend.stage_input(data)
+            off2, total = frontend.front_resident()
+            got = frontend.resident_checksum()
+            frontend.set_emit_mode(EMIT_RAW)
+            assert off2 == off
+            assert total == (sum(s.shape[0] for s in streams) if mode == EMIT_RAW else sum(w.size for w in hosted))
+            assert got == [oracle.word_checksum(w) for w in hosted], mode
+    finally:
+        frontend.set_emit_mode(EMIT_RAW)
+        frontend.set_option(OPT_RESIDENT_CHECKSUM, 0)
 
 
 PACKED = [c for c in CASES if c[0] in ("kat-hello", "kat-run", "bytes-256", "long-repeat", "markov2-200k", "mixed-2MiB+5")]

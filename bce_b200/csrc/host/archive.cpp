@@ -1,6 +1,7 @@
 // archive.cpp -- see archive.hpp.
 #include "archive.hpp"
 
+#include <chrono>
 #include <thread>
 
 namespace bcehost {
@@ -39,7 +40,59 @@ void ArchiveWriter::feed_words(const bce_cse_words& batch, int threads) {
   for (auto& t : pool) t.join();
 }
 
+void ArchiveWriter::worker(int i) {
+  for (;;) {
+    const uint32_t* words;
+    size_t count;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_work_.wait(lk, [&] { return stop_ || job_ready_[i]; });
+      if (stop_ && !job_ready_[i]) return;
+      words = job_words_[i];
+      count = job_count_[i];
+      job_ready_[i] = false;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    streams_[i]->packed(words, count);
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      busy_[i] += dt;
+      if (--jobs_open_ == 0) cv_done_.notify_all();
+    }
+  }
+}
+
+void ArchiveWriter::begin_words(const bce_cse_words& batch) {
+  if (pool_.empty())
+    for (int i = 0; i < 8; ++i) pool_.emplace_back(&ArchiveWriter::worker, this, i);
+  std::lock_guard<std::mutex> lk(mu_);
+  for (int i = 0; i < 8; ++i) {
+    if (!batch.count[i]) continue;
+    job_words_[i] = batch.words[i];
+    job_count_[i] = batch.count[i];
+    job_ready_[i] = true;
+    ++jobs_open_;
+  }
+  cv_work_.notify_all();
+}
+
+void ArchiveWriter::wait_words() {
+  std::unique_lock<std::mutex> lk(mu_);
+  cv_done_.wait(lk, [&] { return jobs_open_ == 0; });
+}
+
+ArchiveWriter::~ArchiveWriter() {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    stop_ = true;
+  }
+  cv_work_.notify_all();
+  for (auto& t : pool_) t.join();
+}
+
 std::vector<uint16_t> ArchiveWriter::finish(uint32_t offset) {
+  wait_words();
   uint32_t total = 0;
   for (auto& s : streams_) {                                        // bce.cpp:1134-1138
     s->finish();

@@ -1,4 +1,5 @@
 // host_api.cpp -- extern "C" surface of libbce_host (include/bce_host.h).
+#include <algorithm>
 #include <cstdlib>
 #include <chrono>
 #include <cstdio>
@@ -56,6 +57,16 @@ int bce_archive_feed(bce_archive_writer* h, const bce_cse_batch* batch, int thre
 int bce_archive_feed_words(bce_archive_writer* h, const bce_cse_words* batch, int threads) {
   if (!h || !batch) return BCE_GPU_E_ARG;
   BCE_HOST_GUARD(h->w->feed_words(*batch, threads);)
+  return BCE_GPU_OK;
+}
+int bce_archive_begin_words(bce_archive_writer* h, const bce_cse_words* batch) {
+  if (!h || !batch) return BCE_GPU_E_ARG;
+  BCE_HOST_GUARD(h->w->begin_words(*batch);)
+  return BCE_GPU_OK;
+}
+int bce_archive_wait(bce_archive_writer* h) {
+  if (!h) return BCE_GPU_E_ARG;
+  h->w->wait_words();
   return BCE_GPU_OK;
 }
 int bce_scan_feed_words(bce_scan* h, const bce_cse_words* batch) {
@@ -150,26 +161,56 @@ int bce_compress_buffer(bce_gpu_ctx* ctx, const uint8_t* T, uint32_t n, const ui
   const auto t1 = clk::now();
   bce_archive_writer* w = bce_archive_begin(n, C, cfg288);          // BCE::encode, bce.cpp:1417
   if (!w) { bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return BCE_GPU_E_NOMEM; }
-  bce_cse_words batch;
-  double gpu_s = 0, code_s = 0;
+  // Double buffering over the context's two pinned batch buffers: while the coder threads work on batch j, the
+  // next call copies batch j+1 out and runs the kernels of batch j+2 (a batch stays valid until the call after
+  // the next one, include/bce_gpu.h).  threads <= 1 keeps the serial form.
+  bce_cse_words cur, nxt;
+  double gpu_s = 0, wait_s = 0;
   size_t nbatch = 0, nw = 0;
-  do {
+  auto fail = [&](int code) { bce_archive_abort(w); bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return code; };
+  {
     const auto a = clk::now();
-    rc = bce_gpu_cse_next_words(ctx, &batch);
-    if (rc) { bce_archive_abort(w); bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return rc; }
-    const auto b = clk::now();
-    bce_archive_feed_words(w, &batch, threads);
-    gpu_s += secs(a, b);
-    code_s += secs(b, clk::now());
+    rc = bce_gpu_cse_next_words(ctx, &cur);
+    gpu_s += secs(a, clk::now());
+    if (rc) return fail(rc);
+  }
+  for (;;) {
     ++nbatch;
-    for (int i = 0; i < 8; ++i) nw += batch.count[i];
-  } while (!batch.done);
+    for (int i = 0; i < 8; ++i) nw += cur.count[i];
+    if (threads <= 1) {
+      const auto a = clk::now();
+      bce_archive_feed_words(w, &cur, 1);
+      wait_s += secs(a, clk::now());
+      if (cur.done) break;
+      const auto b = clk::now();
+      rc = bce_gpu_cse_next_words(ctx, &nxt);
+      gpu_s += secs(b, clk::now());
+      if (rc) return fail(rc);
+    } else {
+      try { w->w->begin_words(cur); } catch (...) { return fail(BCE_GPU_E_NOMEM); }
+      const bool last = cur.done != 0;
+      if (!last) {
+        const auto a = clk::now();
+        rc = bce_gpu_cse_next_words(ctx, &nxt);                    // coders of batch j run under this call
+        gpu_s += secs(a, clk::now());
+      }
+      const auto b = clk::now();
+      w->w->wait_words();
+      wait_s += secs(b, clk::now());
+      if (last) break;
+      if (rc) return fail(rc);
+    }
+    cur = nxt;
+  }
   bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr);
   const auto t2 = clk::now();
+  double busiest = 0;
+  for (int i = 0; i < 8; ++i) busiest = std::max(busiest, w->w->busy_seconds(i));
   rc = bce_archive_finish(w, offset, words, nwords);
   if (timing)
-    std::fprintf(stderr, "[bce] front (H2D + BWT + wavelet) %.3f s | level loop waits %.3f s | coders %.3f s (%d threads, "
-                 "%zu words in %zu batches) | finish %.3f s\n", secs(t0, t1), gpu_s, code_s, threads, nw, nbatch,
+    std::fprintf(stderr, "[bce] front (H2D + BWT + wavelet) %.3f s | in cse_next_words %.3f s (%s the coders) | waiting for "
+                 "the coders after it %.3f s | busiest coder %.3f s (%d threads, %zu words in %zu batches) | finish %.3f s\n",
+                 secs(t0, t1), gpu_s, threads > 1 ? "under" : "not overlapped with", wait_s, busiest, threads, nw, nbatch,
                  secs(t2, clk::now()));
   return rc;
 }

@@ -16,6 +16,7 @@ HOST_SYMBOLS = [
     "bce_scan_begin", "bce_scan_feed", "bce_scan_finish", "bce_compress_buffer", "bce_scan_buffer",
     "bce_host_default_config", "bce_host_free",
     "bce_archive_feed_words", "bce_scan_feed_words", "bce_host_pack_counts", "bce_decode_buffer",
+    "bce_archive_begin_words", "bce_archive_wait",
 ]
 
 
@@ -40,6 +41,8 @@ def load_library() -> C.CDLL:
         lib.bce_host_free.argtypes = [vp]
         lib.bce_archive_feed_words.argtypes = [vp, C.POINTER(CseWords), C.c_int]
         lib.bce_scan_feed_words.argtypes = [vp, C.POINTER(CseWords)]
+        lib.bce_archive_begin_words.argtypes = [vp, C.POINTER(CseWords)]
+        lib.bce_archive_wait.argtypes = [vp]
         lib.bce_host_pack_counts.argtypes = [C.c_int, vp, C.c_int, vp, C.c_size_t, vp]
         lib.bce_host_pack_counts.restype = C.c_size_t
         lib.bce_decode_buffer.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t)]

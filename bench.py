@@ -115,21 +115,30 @@ class ClockSampler:
 # reference arm: the reference's own CPU implementation of the path
 # ---------------------------------------------------------------------------------------------
 def reference_front_seconds(sample, threads: int):
-    """Unmodified reference: RankFile ctor (rotate + BWT + wavelet) + BCE<tap>::encode (the CSE
-    loop, handing every count to a coder that stores the 5 words), through oracle/_ref."""
+    """Unmodified reference: RankFile ctor (rotate + BWT + wavelet) + BCE<tap>::encode (the CSE loop handing
+    every count to a coder that only counts the calls: the reference is not charged for storing them), through
+    oracle/_ref."""
     from oracle import oracle
     os.environ["OMP_NUM_THREADS"] = str(threads)
-    r = oracle.ref_front(sample, want_bwt=False, want_ranks=False, record=True)
+    r = oracle.ref_front(sample, want_bwt=False, want_ranks=False, record=False)
     return r["seconds_rankfile"] + r["seconds_encode"], r
 
 
-def pick_sample_bytes(gen, seed, budget_s: float, threads: int):
-    """Probe on 1 MiB, then size the sample so that one step takes about budget_s seconds."""
+def reference_rate(gen, seed, threads: int):
+    """Bytes per second of the reference front end on a 4 MiB probe (it gets slower with size: an upper bound)."""
     from bce_b200 import synth
-    probe = synth.generate(gen, 1 << 20, seed)
+    probe = synth.generate(gen, 4 << 20, seed)
     t, _ = reference_front_seconds(probe, threads)
-    rate = (1 << 20) / max(t, 1e-3)                     # bytes per second, roughly size-independent
-    return int(max(1 << 20, min(64 << 20, rate * budget_s))), rate
+    return (4 << 20) / max(t, 1e-3)
+
+
+def cpu_sample_bytes(gen, seed, nbytes: int, budget_s: float, threads: int) -> int:
+    """The prefix of the workload the cpu_baseline leg times: about budget_s seconds of reference work."""
+    return int(max(1 << 20, min(nbytes, 64 << 20, reference_rate(gen, seed, threads) * budget_s)))
+
+
+NATIVE_NOTE = ("libbce_synth.so is the synthetic input generator only; the reference arm's compute is "
+               "oracle/_ref/libbce_ref_tap.so = the unmodified /root/reference/bce.cpp")
 
 
 def run_reference(args, rank: int, world: int):
@@ -143,29 +152,44 @@ def run_reference(args, rank: int, world: int):
         return 0
     cores = os.cpu_count() or 1
     threads = min(8, cores)                              # the reference forks over 8 levels at most (bce.cpp:1250)
-    budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
-    sample_bytes, _ = pick_sample_bytes(gen, seed, budget, threads)
+    # The reference gets slower per byte as the input grows (a 32 MB prefix of the 1 GB workload runs 15 % faster per
+    # byte than a 64 MB one), so a prefix is not the configuration.  When one pass over the WHOLE workload fits the
+    # budget it is timed exactly once (steps_run = 1, no warm-up pass: nothing to warm on the host); otherwise the
+    # largest prefix that fits, and `config.sample_bytes` says so in both arms.
+    est_full = nbytes / reference_rate(gen, seed, threads)
+    full = est_full <= args.ref_budget_s
+    if full:
+        sample_bytes, steps_run, warm_run = nbytes, 1, 0
+    else:
+        steps_run, warm_run = max(1, args.steps), min(1, args.warmup)
+        sample_bytes = int(max(1 << 20, min(nbytes, nbytes * args.ref_budget_s / est_full / (steps_run + warm_run))))
     sample = synth.generate(gen, sample_bytes, seed)
-    for _ in range(args.warmup):
+    for _ in range(warm_run):
         reference_front_seconds(sample, threads)
     times = []
-    for _ in range(args.steps):
+    r = None
+    for _ in range(steps_run):
         t, r = reference_front_seconds(sample, threads)
         times.append(t)
     total = sum(times)
-    value = sample_bytes * args.steps / total / 1e6
+    value = sample_bytes * steps_run / total / 1e6
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "steps_run": steps_run, "warmup_run": warm_run,
+        "ms_per_step": 1e3 * total / steps_run,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32",
         "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": args.workload, "generator": gen, "bytes": nbytes, "seed": seed,
-                   "sample_bytes": sample_bytes},
+        "config": {"workload": args.workload, "generator": gen, "bytes_per_gpu": nbytes, "seed": seed,
+                   "sample_bytes": sample_bytes, "whole_workload": full},
+        "stage_s": {"rankfile (rotate + BWT + wavelet)": r["seconds_rankfile"], "encode (CSE loop, counting coder)": r["seconds_encode"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
-                         "sample": f"first {sample_bytes} bytes of {args.workload}; unmodified bce.cpp front end "
-                                   f"(rotate+BWT+wavelet+CSE loop, counts stored by a tap coder); BWT stage is the "
-                                   f"oracle's SA-IS stand-in for libdivsufsort; OMP_NUM_THREADS={threads} of {cores} cores"},
+                         "sample": (f"the whole {args.workload} workload ({nbytes} bytes), one pass" if full else
+                                    f"first {sample_bytes} bytes of {args.workload}") +
+                                   f"; unmodified bce.cpp front end (rotate + BWT + wavelet + CSE loop, counts handed to a "
+                                   f"coder that only counts them); BWT stage is the oracle's SA-IS stand-in for "
+                                   f"libdivsufsort; OMP_NUM_THREADS={threads} of {cores} cores"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "native_note": NATIVE_NOTE,
     }
     print(json.dumps(line))
     return 0
@@ -196,7 +220,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
 
-    from bce_b200 import Frontend, batch, synth
+    from bce_b200 import Frontend, batch, host, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -235,7 +259,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     sampler.start()
     t0 = time.perf_counter()
     dev_ms, stats_list = 0.0, []
+    # the working set (48 n bytes of keys, indices, SA, ranks) exceeds the 126 MB L2 from n = 3 MB on; smaller
+    # inputs get the L2 flushed between steps (a 512 MB buffer written on the device, outside the timed events)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda") if 48 * nbytes < (256 << 20) else None
     for _ in range(args.steps):
+        if flush is not None:
+            flush.fill_(1)
+            torch.cuda.synchronize()
         fe.front_resident()
         st = fe.stats()
         dev_ms += st["ms_total"]
@@ -260,6 +290,26 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     e2e_ms = maxreduce((time.perf_counter() - t0) * 1e3)
     e2e_value = world * nbytes * args.steps / (e2e_ms / 1e3) / 1e6
     st_e2e = fe.stats()
+
+    # ---- `bce -c` as a user runs it: front end + host range coders, archive in memory (rank 0) --------------
+    fe.set_emit_mode(0)
+    e2e_cli = None
+    if rank == 0 and not args.no_cli:
+        t0 = time.perf_counter()
+        arc = host.compress(fe, host_in, threads=8)
+        cli_s = time.perf_counter() - t0
+        e2e_cli = {"seconds": cli_s, "MBps": nbytes / cli_s / 1e6, "archive_bytes": len(arc), "coder_threads": 8,
+                   "host_cores": os.cpu_count(), "what": "bce_compress_buffer: H2D + front end + host range coders "
+                   "(one thread per stream) + archive assembly, one pass, not in the timed region of `value`"}
+        if args.workload == "mixed-256MB":                 # configs[3]: bce -s, then bce -c with the config it wrote
+            t0 = time.perf_counter()
+            cfg = host.scan(fe, host_in)
+            scan_s = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            arc2 = host.compress(fe, host_in, cfg=cfg, threads=8)
+            e2e_cli.update(scan_seconds=scan_s, scan_MBps=nbytes / scan_s / 1e6,
+                           compress_with_config_seconds=time.perf_counter() - t0, archive_with_config_bytes=len(arc2))
+    fe.set_emit_mode(EMIT_CODER)
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
     peak, peak_src = measured_peak_gbs()
@@ -310,7 +360,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if oracle.have_ref():
             cores = os.cpu_count() or 1
             threads = min(8, cores)
-            sample_bytes, _ = pick_sample_bytes(gen, seed, 12.0, threads)
+            sample_bytes = cpu_sample_bytes(gen, seed, nbytes, 12.0, threads)
             sample = synth.generate(gen, sample_bytes, seed)
             t, r = reference_front_seconds(sample, threads)
             cpu_baseline = {"value": sample_bytes / t / 1e6, "unit": UNIT, "cores": threads, "kind": "reference",
@@ -326,7 +376,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
             "config": {"workload": args.workload, "generator": gen, "bytes_per_gpu": nbytes, "seed": seed,
-                       "l2": "working set (12 n bytes of keys + 8 n of SA/rank) exceeds L2; no flush",
+                       "sample_bytes": nbytes, "whole_workload": True,
+                       "l2": "working set (48 n bytes of keys, indices, SA, ranks) exceeds L2; no flush" if flush is None
+                             else "512 MB written on the device between timed steps (L2 flush)",
                        "parallelism": f"replicas x{world} (one input per GPU)"},
             "wall_ms_per_step": wall_ms / args.steps,
             "stage_ms": {k: st[k] for k in ("ms_pack", "ms_radix", "ms_rerank", "ms_rekey", "ms_bwt_gather",
@@ -343,6 +395,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "ms_h2d": st_e2e["ms_h2d"], "ms_d2h": st_e2e["ms_d2h"],
                     "ms_bwt_total": st_e2e["ms_bwt_total"], "ms_cse_total": st_e2e["ms_cse_total"],
                     "cse_launches": st_e2e["cse_launches"]},
+            "e2e_cli": e2e_cli,
+            "native_note": NATIVE_NOTE,
             "gpu_launches": int(sum(s["gpu_launches"] for s in stats_list)),
             "clocks": clocks,
             "per_rank": [vars(g) for g in gathered],
@@ -361,6 +415,9 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--bytes", type=int, default=0, help="override the input size (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true", help="skip the `bce -c` wall-time leg (host coders)")
+    ap.add_argument("--ref-budget-s", type=float, default=420.0,
+                    help="--impl reference: seconds one run may take; the whole workload is timed once when it fits")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

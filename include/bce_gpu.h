@@ -47,7 +47,9 @@ typedef struct bce_tuple {
 } bce_tuple;
 
 /* A batch of emitted counts.  tuples[i] points into pinned host memory owned by the
- * context and stays valid until the next bce_gpu_cse_next / cse_begin / close.
+ * context.  Two buffers alternate: a batch stays valid until the call AFTER the next
+ * bce_gpu_cse_next* returns (or the next cse_begin / close), so a consumer can work on batch j
+ * while the next call fetches batch j+1 (host coders overlapped with the GPU).
  * Stream i = wavelet level i = coder_[i] (bce.cpp:1124).  Concatenating the batches of
  * one stream gives exactly the sequence of set() calls the reference makes on coder_[i]:
  * ascending round of the do..while (bce.cpp:1246), ascending position inside a round. */
@@ -145,7 +147,7 @@ int bce_gpu_cse_next(bce_gpu_ctx *ctx, bce_cse_batch *out);
  * cfg288: 9 x 32 context-bit table (rows 0..7 are used), NULL = default table. */
 enum { BCE_EMIT_RAW = 0, BCE_EMIT_CODER = 1, BCE_EMIT_SCAN = 2 };
 typedef struct bce_cse_words {
-  const uint32_t *words[8];   /* pinned host memory, valid until the next cse_next* call */
+  const uint32_t *words[8];   /* pinned host memory, valid as bce_cse_batch: until the call after the next */
   size_t count[8];            /* words */
   int done;
 } bce_cse_words;

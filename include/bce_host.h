@@ -28,6 +28,11 @@ bce_archive_writer *bce_archive_begin(uint32_t n, const uint32_t C[8], const uin
 int bce_archive_feed(bce_archive_writer *w, const bce_cse_batch *batch, int threads);
 /* same for BCE_EMIT_CODER word batches (the config must be the one given to bce_gpu_set_emit_mode) */
 int bce_archive_feed_words(bce_archive_writer *w, const bce_cse_words *batch, int threads);
+/* Overlapped form: begin hands the batch to one persistent coder thread per stream and returns at once (the
+ * reference forks its eight coders inside the level loop, bce.cpp:1250-1252, :1302); wait blocks until the
+ * batch is coded.  The batch's memory must stay valid until then; one batch in flight at a time. */
+int bce_archive_begin_words(bce_archive_writer *w, const bce_cse_words *batch);
+int bce_archive_wait(bce_archive_writer *w);
 /* flush, header (n, offset, sizes), concatenate; *words is malloc'd (bce_host_free). */
 int bce_archive_finish(bce_archive_writer *w, uint32_t offset, uint16_t **words, size_t *nwords);
 void bce_archive_abort(bce_archive_writer *w);

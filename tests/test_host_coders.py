@@ -53,6 +53,31 @@ def test_scan_config_and_archive_with_config():
     assert arc == oracle.encode_archive(c["C"], c["streams"], len(data), off, cfg=cfg)
 
 
+def test_overlapped_coder_threads_give_the_same_archive():
+    """bce_archive_begin_words / bce_archive_wait (one persistent coder thread per stream, what
+    bce_compress_buffer runs under the GPU's next batch) over several batches == one serial feed."""
+    from bce_b200.gpu import EMIT_CODER
+    lib = host.load_library()
+    cases = dict((c[0], c[1]) for c in small_cases() + medium_cases())
+    for name, pieces in (("kat-hello", 1), ("markov2-200k", 5), ("long-repeat", 3), ("bytes-256", 2)):
+        data = cases[name]
+        off, c = streams_of(data)
+        Cv = (host.C.c_uint32 * 8)(*c["C"])
+        w = lib.bce_archive_begin(len(data), Cv, None)
+        keep = []
+        for p in range(pieces):
+            part = [s[(s.shape[0] * p) // pieces:(s.shape[0] * (p + 1)) // pieces] for s in c["streams"]]
+            b, k = host._words_batch(host.pack_counts(EMIT_CODER, part), done=(p == pieces - 1))
+            keep.append(k)
+            assert lib.bce_archive_begin_words(w, host.C.byref(b)) == 0
+            assert lib.bce_archive_wait(w) == 0
+        words, nw = host.C.c_void_p(), host.C.c_size_t()
+        assert lib.bce_archive_finish(w, off, host.C.byref(words), host.C.byref(nw)) == 0
+        arc = host.C.string_at(words.value, nw.value * 2)
+        lib.bce_host_free(words)
+        assert arc == oracle.compress(data), name
+
+
 def test_wide_ranges_take_the_binary_decomposition():
     """k > 31 symbols (bce.cpp:507-510) and uint32 wrap in the context index (:674)."""
     import numpy as np

@@ -267,7 +267,8 @@ void bce_gpu_close(bce_gpu_ctx* h) {
   bce::cse_destroy(c);
   c->text.release(); c->bwt.release(); c->ranks.release(); c->scratch.release();
   c->small.release(); c->desc.release();
-  c->pinned_small.release(); c->pinned_emit.release(); c->pinned_io.release();
+  c->scan_tmp.release();
+  c->pinned_small.release(); c->pinned_emit.release(); c->pinned_emit2.release(); c->pinned_io.release();
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->pass_ev) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -405,6 +406,20 @@ int bce_gpu_cse_next_words(bce_gpu_ctx* h, bce_cse_words* out) {
   BCE_TRY(next_words(c, &wb));
   for (int i = 0; i < 8; ++i) { out->words[i] = wb.words[i]; out->count[i] = wb.count[i]; }
   out->done = wb.done;
+  return BCE_GPU_OK;
+}
+
+int bce_gpu_cse_next_buckets(bce_gpu_ctx* h, bce_scan_buckets* out) {
+  if (!h || !out) return BCE_GPU_E_ARG;
+  Ctx* c = static_cast<Ctx*>(h);
+  bce::begin_call(c);
+  if (!c->cse_active || c->cse_emit_mode_active != BCE_EMIT_SCAN) {
+    bce::set_error(c, "cse_next_buckets: needs a run started in BCE_EMIT_SCAN mode");
+    return BCE_GPU_E_STATE;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  BCE_TRY(bce::cse_advance_buckets(c, out));
+  c->stats.ms_cse_total += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return BCE_GPU_OK;
 }
 

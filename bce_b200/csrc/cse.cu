@@ -203,6 +203,40 @@ __global__ void __launch_bounds__(256) cse_checksum_kernel(const uint32_t* __res
   if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], s); atomicAdd(&acc[1], ws); }
 }
 
+// ---- bce -s: bucketing of a batch of BCE_EMIT_SCAN words (ScanCoder::set, bce.cpp:737-744) ---------------
+// word = [esc:1|nb:5 @26|q2:8 @18|q1:8 @10|k:5 @5|sym:5]: bits 5..25 are the bucket (k, q1, q2).  The word rides in
+// the upper half of a 64-bit sort key whose low 21 bits are the bucket; the value is the word's position.
+__global__ void __launch_bounds__(256) scan_keys_kernel(const uint32_t* __restrict__ words, uint32_t cnt,
+                                                        uint64_t* __restrict__ key, uint32_t* __restrict__ val,
+                                                        unsigned long long* halvings) {
+  unsigned long long nb = 0;
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < cnt; i += gridDim.x * 256u) {
+    const uint32_t w = words[i];
+    key[i] = (uint64_t(w) << 32) | ((w >> 5) & 0x1FFFFFu);
+    val[i] = i;
+    if (w >> 31) nb += (w >> 26) & 31u;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) nb += __shfl_xor_sync(0xffffffffu, nb, d);
+  if ((threadIdx.x & 31) == 0 && nb) atomicAdd(halvings, nb);
+}
+
+// After the stable sort: symbols as bytes in bucket order; one record per bucket (written where an atomic
+// counter says: the host orders them by `start`, so the order the atomics resolve in does not matter).
+__global__ void __launch_bounds__(256) scan_compact_kernel(const uint64_t* __restrict__ key, const uint32_t* __restrict__ val,
+                                                           uint32_t cnt, uint8_t* __restrict__ syms,
+                                                           bce_scan_bucket* __restrict__ buckets, uint32_t cap, uint32_t* nbuckets) {
+  for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < cnt; i += gridDim.x * 256u) {
+    const uint64_t k = key[i];
+    syms[i] = uint8_t(uint32_t(k >> 32) & 31u);
+    const uint32_t b = uint32_t(k) & 0x1FFFFFu;
+    if (i == 0 || (uint32_t(key[i - 1]) & 0x1FFFFFu) != b) {
+      const uint32_t slot = atomicAdd(nbuckets, 1u);
+      if (slot < cap) buckets[slot] = bce_scan_bucket{b, i, val[i], 0u};
+    }
+  }
+}
+
 // vector load of ITEMS consecutive frontier entries; `rev` = stored back to front
 template <int ITEMS>
 __device__ __forceinline__ void load_items(const uint32_t* base, uint32_t first, bool rev, uint32_t cap, uint32_t (&out)[ITEMS]) {
@@ -972,6 +1006,101 @@ int cse_advance(Ctx* c, bool resident, CseWordBatch* out) {
   c->stats.ms_d2h += ms;
   out->done = this_done ? 1 : 0;
   if (this_done) c->cse_done = true;
+  return BCE_GPU_OK;
+}
+
+// `bce -s`: one batch of counts, bucketed on the device (include/bce_gpu.h, bce_gpu_cse_next_buckets).  The batch is
+// computed, every stream's words are sorted stably by bucket with the suffix sorter's radix passes, symbols and the
+// bucket table go to pinned memory.  No overlap with the next batch's kernels: the host's flush (bce.cpp:751-800,
+// six simulated coders per symbol) is what `bce -s` waits for.
+int cse_advance_buckets(Ctx* c, bce_scan_buckets* out) {
+  if (!c->cse_active || !c->cse) { set_error(c, "cse_next_buckets without cse_begin"); return BCE_GPU_E_STATE; }
+  CseHost* H = c->cse;
+  memset(out, 0, sizeof *out);
+  if (c->cse_done) { out->done = 1; return BCE_GPU_OK; }
+  size_t cnt[8];
+  bool done = false;
+  BCE_TRY(run_batch(c, 0, cnt, &done));
+  cudaStream_t st = c->stream;
+  size_t maxcnt = 0, total = 0, bucket_cap[8], bucket_total = 0;
+  for (int l = 0; l < 8; ++l) {
+    if (cnt[l] > 0xFFFFFFF0ull) { set_error(c, "scan batch of %zu words", cnt[l]); return BCE_GPU_E_INTERNAL; }
+    maxcnt = std::max(maxcnt, cnt[l]);
+    total += (cnt[l] + 15) & ~size_t(15);
+    bucket_cap[l] = std::min<size_t>(cnt[l], size_t(1) << 21);
+    bucket_total += bucket_cap[l];
+  }
+  const size_t need = 2 * Carver::need(maxcnt, 8) + 2 * Carver::need(maxcnt, 4) + Carver::need(total, 1) +
+                      Carver::need(bucket_total, sizeof(bce_scan_bucket)) + 4096;
+  BCE_TRY(c->scan_tmp.ensure(c, need));
+  Carver cv(c->scan_tmp.p, c->scan_tmp.cap);
+  uint64_t* kA = cv.take<uint64_t>(maxcnt);
+  uint64_t* kB = cv.take<uint64_t>(maxcnt);
+  uint32_t* vA = cv.take<uint32_t>(maxcnt);
+  uint32_t* vB = cv.take<uint32_t>(maxcnt);
+  uint8_t* syms = cv.take<uint8_t>(total);
+  bce_scan_bucket* buckets = cv.take<bce_scan_bucket>(bucket_total);
+  struct Counters { unsigned long long halvings[8]; uint32_t nbuckets[8]; };
+  Counters* d_cnt = reinterpret_cast<Counters*>(cv.take<unsigned char>(sizeof(Counters)));
+  if (!cv.ok()) { set_error(c, "scan bucketing: scratch carve failed"); return BCE_GPU_E_NOMEM; }
+  BCE_CUDA(c, cudaMemsetAsync(d_cnt, 0, sizeof(Counters), st));
+  const int shifts[3] = {0, 8, 16};
+  size_t sym_at[8], bucket_at[8], sa = 0, ba = 0;
+  for (int l = 0; l < 8; ++l) {
+    sym_at[l] = sa;
+    bucket_at[l] = ba;
+    sa += (cnt[l] + 15) & ~size_t(15);
+    ba += bucket_cap[l];
+    if (!cnt[l]) continue;
+    const uint32_t m = uint32_t(cnt[l]);
+    const int grid = int(std::min<size_t>((m + 255) / 256, size_t(c->sm_count) * 8));
+    scan_keys_kernel<<<grid, 256, 0, st>>>(H->emit_dev[0][l], m, kA, vA, &d_cnt->halvings[l]);
+    c->stats.gpu_launches++;
+    BCE_CUDA(c, cudaGetLastError());
+    uint64_t* ok = kA;
+    uint32_t* ov = vA;
+    int ran = 0;
+    RadixHistSource stable;
+    stable.stable_first = true;                          // insertion order inside a bucket is what flush() depends on
+    BCE_TRY(radix_sort_pairs(c, kA, kB, vA, vB, m, shifts, 3, &ok, &ov, &ran, &stable));
+    scan_compact_kernel<<<grid, 256, 0, st>>>(ok, ov, m, syms + sym_at[l], buckets + bucket_at[l], uint32_t(bucket_cap[l]),
+                                              &d_cnt->nbuckets[l]);
+    c->stats.gpu_launches++;
+    BCE_CUDA(c, cudaGetLastError());
+  }
+  Counters* h_cnt = reinterpret_cast<Counters*>(c->pinned_small.as<char>() + 44 * 1024);
+  BCE_CUDA(c, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+  BCE_CUDA(c, cudaStreamSynchronize(st));
+  size_t pin_bytes = 64;
+  for (int l = 0; l < 8; ++l) {
+    if (h_cnt->nbuckets[l] > bucket_cap[l]) { set_error(c, "scan bucketing: %u buckets in stream %d", h_cnt->nbuckets[l], l); return BCE_GPU_E_INTERNAL; }
+    pin_bytes += ((cnt[l] + 15) & ~size_t(15)) + size_t(h_cnt->nbuckets[l]) * sizeof(bce_scan_bucket);
+  }
+  PinnedBuf& pin = H->pinned_flip ? c->pinned_emit2 : c->pinned_emit;
+  H->pinned_flip ^= 1;
+  BCE_TRY(pin.ensure(c, pin_bytes));
+  char* hp = pin.as<char>();
+  size_t at = 0;
+  BCE_CUDA(c, cudaEventRecord(c->ev[4], st));
+  for (int l = 0; l < 8; ++l) {
+    out->count[l] = cnt[l];
+    out->nbuckets[l] = h_cnt->nbuckets[l];
+    out->halvings[l] = h_cnt->halvings[l];
+    out->syms[l] = reinterpret_cast<const uint8_t*>(hp + at);
+    if (cnt[l]) BCE_CUDA(c, cudaMemcpyAsync(hp + at, syms + sym_at[l], cnt[l], cudaMemcpyDeviceToHost, st));
+    at += (cnt[l] + 15) & ~size_t(15);
+    out->buckets[l] = reinterpret_cast<const bce_scan_bucket*>(hp + at);
+    const size_t bb = size_t(h_cnt->nbuckets[l]) * sizeof(bce_scan_bucket);
+    if (bb) BCE_CUDA(c, cudaMemcpyAsync(hp + at, buckets + bucket_at[l], bb, cudaMemcpyDeviceToHost, st));
+    at += bb;
+  }
+  BCE_CUDA(c, cudaEventRecord(c->ev[5], st));
+  BCE_CUDA(c, cudaEventSynchronize(c->ev[5]));
+  float ms = 0;
+  BCE_CUDA(c, cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]));
+  c->stats.ms_d2h += ms;
+  out->done = done ? 1 : 0;
+  if (done) c->cse_done = true;
   return BCE_GPU_OK;
 }
 

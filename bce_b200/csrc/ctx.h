@@ -49,6 +49,7 @@ struct Ctx : bce_gpu_ctx {
   PinnedBuf pinned_emit;    // emitted counts handed to the caller (two buffers alternate)
   PinnedBuf pinned_emit2;
   PinnedBuf pinned_io;      // staging for pageable caller buffers
+  DevBuf scan_tmp;          // bce -s: sort buffers, bucketed symbols and bucket tables of one batch
 
   uint32_t desc_tag = 0;    // monotonically increasing pass tag (30 bits used)
 
@@ -105,6 +106,8 @@ struct RadixHistSource {
   const uint32_t* dev_hist = nullptr;     // [npass][256] already counted on the device (e.g. by the kernel that wrote the keys);
                                           // may be Ctx::small + kSmallHist itself
   const uint32_t* host_hist = nullptr;    // [npass][256] known on the host
+  bool stable_first = false;              // every pass stable, the first included: equal keys keep their input order
+                                          // (the suffix sorter does not need that: ties are told apart by later rounds)
 };
 int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uint32_t* valB,
                      uint32_t m, const int* shifts, int npass, uint64_t** out_k, uint32_t** out_v,
@@ -121,6 +124,7 @@ int wavelet_build(Ctx* c, uint32_t n);
 int cse_begin(Ctx* c, uint32_t n);
 struct CseWordBatch { const uint32_t* words[8]; size_t count[8]; int done; };
 int cse_advance(Ctx* c, bool resident, CseWordBatch* out);
+int cse_advance_buckets(Ctx* c, bce_scan_buckets* out);
 void cse_destroy(Ctx* c);
 // unbwt.cu
 int unbwt_run(Ctx* c, uint32_t offset, uint32_t n, uint8_t* out_host);

@@ -133,6 +133,16 @@ void ScanSession::feed_words(const bce_cse_words& batch) {
   for (int i = 0; i < 8; ++i) streams_[i]->packed(batch.words[i], batch.count[i]);
 }
 
+void ScanSession::feed_buckets(const bce_scan_buckets& batch) {
+  std::vector<std::thread> pool;                                    // the eight collectors share nothing
+  for (int i = 0; i < 8; ++i)
+    if (batch.count[i] || batch.halvings[i])
+      pool.emplace_back([this, &batch, i] {
+        streams_[i]->bucketed(batch.syms[i], batch.count[i], batch.buckets[i], batch.nbuckets[i], batch.halvings[i]);
+      });
+  for (auto& t : pool) t.join();
+}
+
 ConfigTable ScanSession::finish() {
   // The reference's ScanCoder::init_ is a zero-initialised static (bce.cpp:833-834) that the
   // nine flush() calls fill: streams 0..7 (bce.cpp:1135-1136) and then the header coder (:1149).

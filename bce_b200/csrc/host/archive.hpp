@@ -50,6 +50,7 @@ class ScanSession {
   ScanSession();
   void feed(const bce_cse_batch& batch);
   void feed_words(const bce_cse_words& batch);                    // BCE_EMIT_SCAN batches
+  void feed_buckets(const bce_scan_buckets& batch);               // batches bucketed on the device, one thread per stream
   ConfigTable finish();
 
  private:

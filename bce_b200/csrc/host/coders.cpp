@@ -2,6 +2,8 @@
 // reproduces (bce.cpp:line); the arithmetic must match bit for bit.
 #include "coders.hpp"
 
+#include <algorithm>
+
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -276,6 +278,37 @@ void ScanCollector::packed(const uint32_t* words, size_t count) {
       for (uint32_t nb = (w >> 26) & 31u; nb; --nb) nats_ += std::log(2);         // one addition per halving, as :739
     const uint32_t sym = w & 31u, k = (w >> 5) & 31u, q1 = (w >> 10) & 255u, q2 = (w >> 18) & 255u;
     stat_[k][(q2 << 16) | q1].push_back(uint8_t(sym));
+  }
+}
+
+// The same state the calls of count() in stream order would leave.  What flush() (below) reads is, per (k, key), the
+// symbols in insertion order -- the runs arrive in that order, the device sort is stable and batches are fed in
+// order -- and, because it walks an unordered_map, the ORDER IN WHICH THE KEYS OF ONE k WERE FIRST INSERTED
+// (libstdc++ links a new node at the head of its bucket; later insertions into an existing key change nothing):
+// new keys are inserted by ascending position of their first count.  nats_ only ever receives log 2 before flush
+// (:739), so `halvings` equal additions reproduce it exactly.
+void ScanCollector::bucketed(const uint8_t* syms, size_t count, const bce_scan_bucket* buckets, size_t nbuckets,
+                             uint64_t halvings) {
+  for (uint64_t i = 0; i < halvings; ++i) nats_ += std::log(2);
+  if (!nbuckets) return;
+  std::vector<bce_scan_bucket> by_first(buckets, buckets + nbuckets), by_start(buckets, buckets + nbuckets);
+  std::sort(by_first.begin(), by_first.end(), [](const bce_scan_bucket& a, const bce_scan_bucket& b) { return a.first < b.first; });
+  std::sort(by_start.begin(), by_start.end(), [](const bce_scan_bucket& a, const bce_scan_bucket& b) { return a.start < b.start; });
+  auto split = [](uint32_t key21, uint32_t& k, uint32_t& key) {
+    k = key21 & 31u;
+    key = (((key21 >> 13) & 255u) << 16) | ((key21 >> 5) & 255u);             // (q2 << 16) | q1, bce.cpp:743
+  };
+  for (const bce_scan_bucket& b : by_first) {                                  // first appearances, in stream order
+    uint32_t k, key;
+    split(b.key, k, key);
+    stat_[k][key];
+  }
+  for (size_t j = 0; j < by_start.size(); ++j) {
+    uint32_t k, key;
+    split(by_start[j].key, k, key);
+    const size_t a = by_start[j].start, e = j + 1 < by_start.size() ? by_start[j + 1].start : count;
+    std::vector<uint8_t>& v = stat_[k][key];
+    v.insert(v.end(), syms + a, syms + e);
   }
 }
 

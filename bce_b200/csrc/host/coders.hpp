@@ -14,6 +14,8 @@
 // These stay on the host by design (north_star): they are serial per stream.
 #pragma once
 
+#include "../../../include/bce_gpu.h"
+
 #include <array>
 #include <cstdint>
 #include <string>
@@ -135,6 +137,8 @@ class ScanCollector {
   explicit ScanCollector(int id) : row_(id < 0 || id > 7 ? 8 : id) {}
   void count(uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2, uint32_t cs);   // bce.cpp:737-744
   void packed(const uint32_t* words, size_t count);                              // BCE_EMIT_SCAN words
+  // a batch bucketed on the device (bce_gpu_cse_next_buckets): runs of symbol bytes per (k, key)
+  void bucketed(const uint8_t* syms, size_t count, const bce_scan_bucket* buckets, size_t nbuckets, uint64_t halvings);
   // bce.cpp:751-800: fills table[row] and prints "Result size: %.1f B"
   void finish(ConfigTable& table);
 

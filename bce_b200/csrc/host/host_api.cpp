@@ -74,6 +74,11 @@ int bce_scan_feed_words(bce_scan* h, const bce_cse_words* batch) {
   BCE_HOST_GUARD(h->s->feed_words(*batch);)
   return BCE_GPU_OK;
 }
+int bce_scan_feed_buckets(bce_scan* h, const bce_scan_buckets* batch) {
+  if (!h || !batch) return BCE_GPU_E_ARG;
+  BCE_HOST_GUARD(h->s->feed_buckets(*batch);)
+  return BCE_GPU_OK;
+}
 size_t bce_host_pack_counts(int mode, const uint8_t* cfg288, int stream, const bce_tuple* t, size_t count, uint32_t* words) {
   if (!config_ok(cfg288) || stream < 0 || stream > 7) return 0;
   ConfigTable tab = table_from(cfg288);
@@ -223,11 +228,13 @@ int bce_scan_buffer(bce_gpu_ctx* ctx, const uint8_t* T, uint32_t n, uint8_t cfg2
   if (rc) { bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return rc; }
   bce_scan* s = bce_scan_begin();
   if (!s) { bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return BCE_GPU_E_NOMEM; }
-  bce_cse_words batch;
+  // the counts arrive bucketed by (k, context key) from the device; the host appends runs of symbol bytes and
+  // runs ScanCoder's flush unchanged (bce.cpp:751-800)
+  bce_scan_buckets batch;
   do {
-    rc = bce_gpu_cse_next_words(ctx, &batch);
+    rc = bce_gpu_cse_next_buckets(ctx, &batch);
+    if (!rc) rc = bce_scan_feed_buckets(s, &batch);
     if (rc) { delete s->s; delete s; bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return rc; }
-    bce_scan_feed_words(s, &batch);
   } while (!batch.done);
   bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr);
   return bce_scan_finish(s, cfg288_out);

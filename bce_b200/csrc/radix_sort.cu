@@ -354,7 +354,7 @@ int radix_sort_pairs(Ctx* c, uint64_t* keyA, uint64_t* keyB, uint32_t* valA, uin
   constexpr int RS_THREADS = kRadixThreads, RS_TILE = kRadixThreads * kRadixItems;
   constexpr size_t rs_smem = kRadixSmem;
   const uint32_t tiles = (m + RS_TILE - 1) / RS_TILE;
-  const bool unordered_first = exp_env("BCE_GPU_RADIX_STABLE_FIRST", 0) == 0;
+  const bool unordered_first = exp_env("BCE_GPU_RADIX_STABLE_FIRST", 0) == 0 && !(src && src->stable_first);
   const double ballot_above = double(exp_env("BCE_GPU_RADIX_BALLOT_ABOVE", 24));
   int ran = 0;
   for (int p = 0; p < npass; ++p) {

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "bce_gpu_wavelet", "bce_gpu_cse_begin", "bce_gpu_cse_next", "bce_gpu_compress_front",
     "bce_gpu_stage_input", "bce_gpu_front_resident", "bce_gpu_unbwt",
     "bce_gpu_set_emit_mode", "bce_gpu_cse_next_words", "bce_gpu_set_option",
-    "bce_gpu_resident_checksum",
+    "bce_gpu_resident_checksum", "bce_gpu_cse_next_buckets",
 ]
 OPT_EMIT_BATCH_BYTES, OPT_LOCAL_SORT_MIN, OPT_RESIDENT_CHECKSUM = 1, 2, 3
 
@@ -48,6 +48,16 @@ class CseBatch(C.Structure):
 
 class CseWords(C.Structure):
     _fields_ = [("words", C.POINTER(C.c_uint32) * 8), ("count", C.c_size_t * 8), ("done", C.c_int)]
+
+
+class ScanBucket(C.Structure):
+    _fields_ = [("key", C.c_uint32), ("start", C.c_uint32), ("first", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class ScanBuckets(C.Structure):
+    _fields_ = [("syms", C.POINTER(C.c_uint8) * 8), ("count", C.c_size_t * 8),
+                ("buckets", C.POINTER(ScanBucket) * 8), ("nbuckets", C.c_size_t * 8),
+                ("halvings", C.c_uint64 * 8), ("done", C.c_int)]
 
 
 EMIT_RAW, EMIT_CODER, EMIT_SCAN = 0, 1, 2
@@ -103,6 +113,7 @@ def load_library() -> C.CDLL:
     lib.bce_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.bce_gpu_set_scratch_limit.argtypes = [vp, C.c_size_t]
     lib.bce_gpu_set_option.argtypes = [vp, C.c_int, C.c_uint64]
+    lib.bce_gpu_cse_next_buckets.argtypes = [vp, C.POINTER(ScanBuckets)]
     lib.bce_gpu_resident_checksum.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.bce_gpu_bwt.argtypes = [vp, vp, u32, vp, u32p, vp]
     lib.bce_gpu_wavelet.argtypes = [vp, vp, u32, C.POINTER(vp), u32p]
@@ -277,6 +288,35 @@ class Frontend:
                     break
         finally:
             self.set_emit_mode(EMIT_RAW)
+
+    def compress_front_buckets(self, data):
+        """`bce -s` front end: (offset, C[8], batches); a batch is a list of 8 tuples (syms uint8 array, buckets
+        structured array with fields key / start / first, halvings) as bce_gpu_cse_next_buckets returns them."""
+        T = _as_u8(data)
+        self.set_emit_mode(EMIT_SCAN)
+        try:
+            off = C.c_uint32()
+            Cv = (C.c_uint32 * 8)()
+            self._check(self.lib.bce_gpu_compress_front(self.h, T.ctypes.data, T.size, C.byref(off), Cv))
+            batches = []
+            b = ScanBuckets()
+            dt = np.dtype([("key", "<u4"), ("start", "<u4"), ("first", "<u4"), ("reserved", "<u4")])
+            while True:
+                self._check(self.lib.bce_gpu_cse_next_buckets(self.h, C.byref(b)))
+                one = []
+                for i in range(8):
+                    cnt, nb = int(b.count[i]), int(b.nbuckets[i])
+                    syms = (np.ctypeslib.as_array((C.c_uint8 * cnt).from_address(C.addressof(b.syms[i].contents))).copy()
+                            if cnt else np.zeros(0, dtype=np.uint8))
+                    bk = (np.frombuffer((C.c_uint8 * (16 * nb)).from_address(C.addressof(b.buckets[i].contents)), dtype=dt).copy()
+                          if nb else np.zeros(0, dtype=dt))
+                    one.append((syms, bk, int(b.halvings[i])))
+                batches.append(one)
+                if b.done:
+                    break
+        finally:
+            self.set_emit_mode(EMIT_RAW)
+        return int(off.value), [int(x) for x in Cv], batches
 
     def compress_front_discard(self, data):
         """Same call sequence a consumer makes (fused front end, then batches until done) in the

@@ -6,7 +6,7 @@ from pathlib import Path
 
 import numpy as np
 
-from .gpu import CseBatch, CseWords, Tuple5
+from .gpu import CseBatch, CseWords, ScanBucket, ScanBuckets, Tuple5
 
 _LIB_PATH = Path(__file__).resolve().parent / "libbce_host.so"
 _lib = None
@@ -16,7 +16,7 @@ HOST_SYMBOLS = [
     "bce_scan_begin", "bce_scan_feed", "bce_scan_finish", "bce_compress_buffer", "bce_scan_buffer",
     "bce_host_default_config", "bce_host_free",
     "bce_archive_feed_words", "bce_scan_feed_words", "bce_host_pack_counts", "bce_decode_buffer",
-    "bce_archive_begin_words", "bce_archive_wait",
+    "bce_archive_begin_words", "bce_archive_wait", "bce_scan_feed_buckets",
 ]
 
 
@@ -41,6 +41,7 @@ def load_library() -> C.CDLL:
         lib.bce_host_free.argtypes = [vp]
         lib.bce_archive_feed_words.argtypes = [vp, C.POINTER(CseWords), C.c_int]
         lib.bce_scan_feed_words.argtypes = [vp, C.POINTER(CseWords)]
+        lib.bce_scan_feed_buckets.argtypes = [vp, C.POINTER(ScanBuckets)]
         lib.bce_archive_begin_words.argtypes = [vp, C.POINTER(CseWords)]
         lib.bce_archive_wait.argtypes = [vp]
         lib.bce_host_pack_counts.argtypes = [C.c_int, vp, C.c_int, vp, C.c_size_t, vp]
@@ -133,6 +134,49 @@ def scan_config_words(word_streams) -> bytes:
     s = lib.bce_scan_begin()
     b, keep = _words_batch(word_streams)
     lib.bce_scan_feed_words(s, C.byref(b))
+    out = np.zeros(288, dtype=np.uint8)
+    rc = lib.bce_scan_finish(s, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"bce_scan_finish failed: {rc}")
+    return out.tobytes()
+
+
+def bucket_scan_words(words):
+    """What the device does to one stream's BCE_EMIT_SCAN words of a batch (csrc/cse.cu, cse_advance_buckets), in
+    numpy: stable sort by the bucket bits 5..25 -> (syms, buckets[key, start, first], halvings)."""
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    key = (w >> np.uint32(5)) & np.uint32(0x1FFFFF)
+    order = np.argsort(key, kind="stable")
+    ks = key[order]
+    heads = np.flatnonzero(np.concatenate([[True], ks[1:] != ks[:-1]])) if w.size else np.zeros(0, dtype=np.int64)
+    dt = np.dtype([("key", "<u4"), ("start", "<u4"), ("first", "<u4"), ("reserved", "<u4")])
+    bk = np.zeros(heads.size, dtype=dt)
+    bk["key"], bk["start"], bk["first"] = ks[heads], heads, order[heads]
+    esc = (w >> np.uint32(31)) != 0
+    halvings = int(((w[esc] >> np.uint32(26)) & np.uint32(31)).sum())
+    return (w[order] & np.uint32(31)).astype(np.uint8), bk, halvings
+
+
+def scan_config_buckets(batches) -> bytes:
+    """Scan config from batches bucketed as bce_gpu_cse_next_buckets does: batches[b][stream] = (syms, buckets, halvings)."""
+    lib = load_library()
+    s = lib.bce_scan_begin()
+    for bi, one in enumerate(batches):
+        b = ScanBuckets()
+        keep = []
+        for i, (syms, bk, halv) in enumerate(one):
+            sy = np.ascontiguousarray(syms, dtype=np.uint8)
+            bb = np.ascontiguousarray(bk)
+            keep += [sy, bb]
+            b.count[i], b.nbuckets[i], b.halvings[i] = sy.size, bb.size, halv
+            if sy.size:
+                b.syms[i] = C.cast(sy.ctypes.data, C.POINTER(C.c_uint8))
+            if bb.size:
+                b.buckets[i] = C.cast(bb.ctypes.data, C.POINTER(ScanBucket))
+        b.done = 1 if bi == len(batches) - 1 else 0
+        rc = lib.bce_scan_feed_buckets(s, C.byref(b))
+        if rc != 0:
+            raise RuntimeError(f"bce_scan_feed_buckets failed: {rc}")
     out = np.zeros(288, dtype=np.uint8)
     rc = lib.bce_scan_finish(s, out.ctypes.data)
     if rc != 0:

@@ -154,6 +154,30 @@ typedef struct bce_cse_words {
 int bce_gpu_set_emit_mode(bce_gpu_ctx *ctx, int mode, const uint8_t *cfg288);
 int bce_gpu_cse_next_words(bce_gpu_ctx *ctx, bce_cse_words *out);
 
+/* ---- `bce -s`: counts bucketed on the device ------------------------------------------------
+ * ScanCoder::set (bce.cpp:737-744) appends every symbol to stat_[k][(q2 << 16) | q1]; its flush
+ * (:751-800) needs, per (k, key), the symbols in insertion order, and the keys of one k in the order
+ * of their first appearance (it walks an unordered_map).  In BCE_EMIT_SCAN mode this call returns a
+ * batch already bucketed -- a stable device sort of the batch's words by (k, q1, q2):
+ *   syms[i]     one byte per count, bucket after bucket, insertion order inside a bucket
+ *   buckets[i]  one record per (k, key) present in the batch, in no particular order:
+ *               key = k | q1 << 5 | q2 << 13, start = index of its first byte in syms[i], first =
+ *               position in the batch's stream of the count that opened the bucket
+ *   halvings[i] how often the reference would have added log 2 for k > 31 (:738-741)
+ * so the host only appends runs of bytes and runs the unchanged flush.  Same validity as bce_cse_words. */
+typedef struct bce_scan_bucket {
+  uint32_t key, start, first, reserved;
+} bce_scan_bucket;
+typedef struct bce_scan_buckets {
+  const uint8_t *syms[8];
+  size_t count[8];
+  const bce_scan_bucket *buckets[8];
+  size_t nbuckets[8];
+  uint64_t halvings[8];
+  int done;
+} bce_scan_buckets;
+int bce_gpu_cse_next_buckets(bce_gpu_ctx *ctx, bce_scan_buckets *out);
+
 /* ---- fused front end -------------------------------------------------------------
  * bce_gpu_bwt + bce_gpu_cse_begin without the BWT leaving the device: what
  * `RankFile file{...}` (bce.cpp:1411) plus the start of BCE::encode do.  Follow with

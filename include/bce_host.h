@@ -43,6 +43,7 @@ typedef struct bce_scan bce_scan;
 bce_scan *bce_scan_begin(void);
 int bce_scan_feed(bce_scan *s, const bce_cse_batch *batch);
 int bce_scan_feed_words(bce_scan *s, const bce_cse_words *batch);   /* BCE_EMIT_SCAN batches */
+int bce_scan_feed_buckets(bce_scan *s, const bce_scan_buckets *batch);   /* bce_gpu_cse_next_buckets batches */
 int bce_scan_finish(bce_scan *s, uint8_t cfg288_out[288]);
 
 /* whole pipelines over a memory buffer, GPU front end + host coders */

@@ -4,6 +4,7 @@ Bit-exact is the bar: integers, bytes and indices only on this path."""
 import numpy as np
 import pytest
 
+from bce_b200 import host
 from oracle import oracle
 from tests.inputs import medium_cases, small_cases
 
@@ -126,6 +127,45 @@ def test_resident_matches_hosted(frontend):
     finally:
         frontend.set_emit_mode(EMIT_RAW)
         frontend.set_option(OPT_RESIDENT_CHECKSUM, 0)
+
+
+def test_scan_buckets_from_the_device(frontend):
+    """bce_gpu_cse_next_buckets: per stream and (k, key) the device's runs of symbol bytes, joined over
+    the batches, are the stream's SCAN words of that bucket in order; keys first appear in stream order; the
+    halvings add up.  Small batches force several of them."""
+    from bce_b200 import synth
+    from bce_b200.gpu import EMIT_SCAN, OPT_EMIT_BATCH_BYTES
+    for kind, n, seed in (("markov2-text", 300_000, 3), ("mixed-binary", (1 << 20) + 77, 4)):
+        data = synth.generate(kind, n, seed).tobytes()
+        _, _, words = frontend.compress_front_words(data, EMIT_SCAN)
+        frontend.set_option(OPT_EMIT_BATCH_BYTES, 4 << 20)
+        try:
+            _, _, batches = frontend.compress_front_buckets(data)
+        finally:
+            frontend.set_option(OPT_EMIT_BATCH_BYTES, 0)
+        assert len(batches) > 1
+        for i in range(8):
+            want_syms, want_bk, want_halv = host.bucket_scan_words(words[i])
+            want = {}
+            ends = list(want_bk["start"][1:]) + [want_syms.size]
+            for b, e in zip(want_bk, ends):
+                want[int(b["key"])] = want_syms[int(b["start"]):int(e)].tobytes()
+            order_want = [int(k) for k in want_bk["key"][np.argsort(want_bk["first"], kind="stable")]]
+            got, order_got, halv, seen = {}, [], 0, 0
+            for one in batches:
+                syms, bk, h = one[i]
+                halv += h
+                bs = bk[np.argsort(bk["start"], kind="stable")]
+                ends = list(bs["start"][1:]) + [syms.size]
+                for b, e in zip(bs, ends):
+                    got[int(b["key"])] = got.get(int(b["key"]), b"") + syms[int(b["start"]):int(e)].tobytes()
+                for b in bk[np.argsort(bk["first"], kind="stable")]:
+                    if int(b["key"]) not in order_got:
+                        order_got.append(int(b["key"]))
+                seen += syms.size
+            assert seen == words[i].size and halv == want_halv, i
+            assert got == want, i
+            assert order_got == order_want, i
 
 
 PACKED = [c for c in CASES if c[0] in ("kat-hello", "kat-run", "bytes-256", "long-repeat", "markov2-200k", "mixed-2MiB+5")]

@@ -53,6 +53,31 @@ def test_scan_config_and_archive_with_config():
     assert arc == oracle.encode_archive(c["C"], c["streams"], len(data), off, cfg=cfg)
 
 
+def test_bucketed_scan_batches_give_the_same_config(capfd):
+    """`bce -s` with the counts bucketed before they reach the host (what the device does, restated in numpy by
+    host.bucket_scan_words): same 288 bytes as the reference's config and the same nine "Result size" lines as
+    the collector fed count by count -- the cost sums depend on the unordered_map's iteration order."""
+    from bce_b200.gpu import EMIT_SCAN
+    g = json.loads((GOLD / "scan_markov2_200k.json").read_text())
+    cases = dict((c[0], c[1]) for c in small_cases() + medium_cases())
+    for name, pieces in ((g["input"], 1), (g["input"], 4), ("mixed-2MiB+5", 3), ("kat-run", 1)):
+        data = cases[name]
+        off, c = streams_of(data)
+        capfd.readouterr()
+        want = host.scan_config(c["streams"])
+        lines_want = capfd.readouterr().out
+        batches = []
+        for p in range(pieces):
+            part = [s[(s.shape[0] * p) // pieces:(s.shape[0] * (p + 1)) // pieces] for s in c["streams"]]
+            batches.append([host.bucket_scan_words(w) for w in host.pack_counts(EMIT_SCAN, part)])
+        got = host.scan_config_buckets(batches)
+        lines_got = capfd.readouterr().out
+        assert got == want, (name, pieces)
+        assert lines_got == lines_want and lines_got.count("Result size") == 9, (name, pieces)
+        if name == g["input"]:
+            assert got.hex() == g["config_hex"]
+
+
 def test_overlapped_coder_threads_give_the_same_archive():
     """bce_archive_begin_words / bce_archive_wait (one persistent coder thread per stream, what
     bce_compress_buffer runs under the GPU's next batch) over several batches == one serial feed."""

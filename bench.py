@@ -286,10 +286,21 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     counts = 0
     for _ in range(args.steps):
         _, counts = fe.compress_front_discard(host_in)
+    my_e2e_ms = (time.perf_counter() - t0) * 1e3            # this rank alone, before it waits for the others
     barrier()
     e2e_ms = maxreduce((time.perf_counter() - t0) * 1e3)
     e2e_value = world * nbytes * args.steps / (e2e_ms / 1e3) / 1e6
     st_e2e = fe.stats()
+    # every rank's own e2e numbers (the job's e2e is the slowest rank's): where the time of a slow rank goes
+    my_e2e = {"rank": rank, "e2e_ms_per_step": my_e2e_ms / args.steps, "ms_h2d": st_e2e["ms_h2d"], "ms_d2h": st_e2e["ms_d2h"],
+              "ms_bwt_total": st_e2e["ms_bwt_total"], "ms_cse_total": st_e2e["ms_cse_total"],
+              "d2h_GBps": (int(counts) * 4 / 1e9) / (st_e2e["ms_d2h"] / 1e3) if st_e2e["ms_d2h"] > 0 else None,
+              "h2d_GBps": (nbytes / 1e9) / (st_e2e["ms_h2d"] / 1e3) if st_e2e["ms_h2d"] > 0 else None}
+    if world > 1:
+        e2e_ranks = [None] * world
+        dist.all_gather_object(e2e_ranks, my_e2e)
+    else:
+        e2e_ranks = [my_e2e]
 
     # ---- `bce -c` as a user runs it: front end + host range coders, archive in memory (rank 0) --------------
     fe.set_emit_mode(0)
@@ -394,7 +405,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "d2h_bytes_per_step": int(counts) * 4 + 64, "emission": "BCE_EMIT_CODER packed words", "ms_per_step": e2e_ms / args.steps,
                     "ms_h2d": st_e2e["ms_h2d"], "ms_d2h": st_e2e["ms_d2h"],
                     "ms_bwt_total": st_e2e["ms_bwt_total"], "ms_cse_total": st_e2e["ms_cse_total"],
-                    "cse_launches": st_e2e["cse_launches"]},
+                    "cse_launches": st_e2e["cse_launches"],
+                    "per_rank": e2e_ranks,
+                    "aggregate_d2h_GBps": sum(int(counts) * 4 for _ in range(world)) / 1e9 / (e2e_ms / args.steps / 1e3),
+                    "note": "ms_d2h is copy time on the copy stream; it runs under the level-loop kernels of the next "
+                            "batch, so the step is max(kernels, copies) per batch, not their sum"},
             "e2e_cli": e2e_cli,
             "native_note": NATIVE_NOTE,
             "gpu_launches": int(sum(s["gpu_launches"] for s in stats_list)),

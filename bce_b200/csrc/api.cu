@@ -302,6 +302,9 @@ int bce_gpu_set_option(bce_gpu_ctx* h, int option, uint64_t value) {
     case BCE_GPU_OPT_LOCAL_SORT_MIN:
       c->local_sort_min = value ? uint32_t(value > 0xFFFFFFFFull ? 0xFFFFFFFFull : value) : 1u << 20;
       return BCE_GPU_OK;
+    case BCE_GPU_OPT_SLOT_ENTER_NODES:
+      c->slot_enter_nodes = value ? value : 2000000;
+      return BCE_GPU_OK;
     case BCE_GPU_OPT_RESIDENT_CHECKSUM:
       c->resident_checksum = value != 0;
       return BCE_GPU_OK;

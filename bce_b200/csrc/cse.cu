@@ -36,7 +36,10 @@ namespace cg = cooperative_groups;
 
 namespace bce {
 
-constexpr int CS_THREADS = 256;
+#ifndef BCE_CS_THREADS
+#define BCE_CS_THREADS 256
+#endif
+constexpr int CS_THREADS = BCE_CS_THREADS;   // threads of a wide-kernel CTA
 constexpr int CS_MAX_TILE = CS_THREADS * 4;
 
 enum : uint32_t { kCseRunning = 0, kCseDone = 1, kCseDrain = 2, kCseOverflow = 3, kCseRunaway = 4,
@@ -255,6 +258,10 @@ __device__ __forceinline__ void load_items(const uint32_t* base, uint32_t first,
 }  // namespace bce
 
 #include "cse_wide.cuh"   // cse_wide_kernel<ITEMS>: the software-pipelined wide kernel
+#include "cse_slots.cuh"  // cse_slots_kernel: huge frontiers, per-chunk output slots, warps that never wait
+#ifdef BCE_GPU_EXPERIMENTS
+#include "cse_probe.cuh"  // timing probe: one round with fully independent warps
+#endif
 
 namespace bce {
 
@@ -636,6 +643,12 @@ struct CseHost {
   bool finished = false;                 // the level loop terminated
   uint32_t desc_epoch = 0;               // round >> 29 at which the descriptors were last cleared
   unsigned long long sum_words[8] = {};  // resident checksum: words of every stream summed so far
+  // huge frontiers: slot layout (cse_slots.cuh)
+  SlotArgs slot = {};
+  bool slots_ok = false;                 // memory for the slot layout was set aside
+  bool in_slots = false;                 // the frontier currently lives in slots (else flat layout)
+  const void* slot_fn = nullptr;
+  int slot_grid = 0;
 };
 
 static size_t env_size(const char* name, size_t dflt) { return exp_env(name, dflt); }   // experiment builds only
@@ -662,10 +675,42 @@ int cse_begin(Ctx* c, uint32_t n) {
   const size_t cap_full = ((size_t(n) / 2 + 4) + 3) & ~size_t(3);
   size_t cap = cap_full;
   auto frontier_bytes = [](size_t cp) { return 48 * Carver::need(cp, 4); };
+  // Inputs whose frontier can reach millions of nodes keep it in the slot layout while it is that large
+  // (cse_slots.cuh); the flat layout then only has to hold what the other kernels see: at most kSlotLeave nodes
+  // coming back plus one doubling before the host switches over again.
+  const size_t kFlatCapWithSlots = std::max<size_t>(size_t(16) << 20, size_t(4) * c->slot_enter_nodes);
+  const bool want_slots = uint64_t(n) >= 8 * c->slot_enter_nodes && env_size("BCE_GPU_NO_SLOTS", 0) == 0;
+  if (want_slots && cap > kFlatCapWithSlots) cap = kFlatCapWithSlots;
   while (cap > 4096 && frontier_bytes(cap) > budget / 2) cap = (cap / 2 + 3) & ~size_t(3);
   const size_t desc_tiles = 8 * (cap / CS_THREADS + 2);      // sized for the smallest tile of any variant
   const size_t desc_bytes = Carver::need(3 * desc_tiles, 8);
-  const size_t left = budget > frontier_bytes(cap) + desc_bytes ? budget - frontier_bytes(cap) - desc_bytes : 0;
+  size_t left = budget > frontier_bytes(cap) + desc_bytes ? budget - frontier_bytes(cap) - desc_bytes : 0;
+  // slot layout: two node arenas (3 x 4 B per place), E-slots, directories -- from half of what is left
+  size_t arena_cap = 0, chunk_cap = 0, dir_cap = 0, slot_bytes = 0;
+  int slot_grid = 0;
+  if (want_slots) {
+    const void* fn = a.emit_mode == kEmitRaw ? (const void*)cse_slots_kernel<5> : (const void*)cse_slots_kernel<2>;
+    int per_sm = 0;
+    BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SL_THREADS, 0));
+    slot_grid = per_sm * c->sm_count;
+    H->slot_fn = fn;
+    const size_t per_place = 2 * 12 + (wmax * 4) / 2 + 1;   // arenas + E-slot share (one E-slot per 2 places) + directories
+    arena_cap = std::min<size_t>(size_t(4) * n + 4096, (left / 2) / per_place);
+    arena_cap = std::min<size_t>(arena_cap, 0xFFFF0000ull) & ~size_t(SL_CH - 1);
+    chunk_cap = arena_cap / (2 * SL_CH) + 16;
+    dir_cap = 2 * chunk_cap + 64;
+    slot_bytes = 6 * Carver::need(arena_cap, 4) + Carver::need(chunk_cap * SL_CH * wmax, 4) + Carver::need(chunk_cap, 2) +
+                 2 * Carver::need(dir_cap, 1) + 4 * Carver::need(dir_cap, 4) + Carver::need(size_t(16) * slot_grid, 4) +
+                 Carver::need(1, sizeof(SlotState)) + 4096;
+    if (slot_grid < 1 || arena_cap < 8 * c->slot_enter_nodes || slot_bytes > left) { slot_bytes = 0; }
+    else left -= slot_bytes;
+  }
+  H->slots_ok = slot_bytes != 0;
+  H->in_slots = false;
+  if (want_slots && !H->slots_ok) {          // no room for the slot layout: the flat layout has to hold everything
+    cap = cap_full;
+    while (cap > 4096 && frontier_bytes(cap) > budget / 2) cap = (cap / 2 + 3) & ~size_t(3);
+  }
   H->sets = (c->cse_resident || env_size("BCE_GPU_NO_OVERLAP", 0)) ? 1 : 2;
   // words handed back per batch and stream: small batches let the copy of batch k overlap the
   // kernels of batch k+1 (two pinned buffers of this size alternate)
@@ -674,7 +719,7 @@ int cse_begin(Ctx* c, uint32_t n) {
   const size_t per_level_min = (cap + CS_MAX_TILE) * wmax;   // one round must always fit
   if (ew * 8 * 4 * H->sets > left) ew = left / (8 * 4 * H->sets);
   if (ew < per_level_min) ew = per_level_min;
-  const size_t need = frontier_bytes(cap) + desc_bytes + size_t(H->sets) * 8 * Carver::need(ew, 4) + 4096;
+  const size_t need = frontier_bytes(cap) + desc_bytes + size_t(H->sets) * 8 * Carver::need(ew, 4) + slot_bytes + 4096;
   BCE_TRY(c->scratch.ensure(c, need));
   Carver cv(c->scratch.p, c->scratch.cap);
   for (int p = 0; p < 2; ++p)
@@ -686,6 +731,25 @@ int cse_begin(Ctx* c, uint32_t n) {
   a.desc = cv.take<uint64_t>(3 * desc_tiles);
   for (int s = 0; s < H->sets; ++s)
     for (int l = 0; l < 8; ++l) H->emit_dev[s][l] = cv.take<uint32_t>(ew);
+  if (H->slots_ok) {
+    SlotArgs& sl = H->slot;
+    for (int p = 0; p < 2; ++p) {
+      sl.ns[p] = cv.take<uint32_t>(arena_cap);
+      sl.na[p] = cv.take<uint32_t>(arena_cap);
+      sl.nb[p] = cv.take<uint32_t>(arena_cap);
+      sl.cnt[p] = cv.take<uint8_t>(dir_cap);
+      sl.P[p] = cv.take<uint32_t>(dir_cap);
+      sl.start[p] = cv.take<uint32_t>(dir_cap);
+    }
+    sl.eslot = cv.take<uint32_t>(chunk_cap * SL_CH * wmax);
+    sl.ecnt = cv.take<uint16_t>(chunk_cap);
+    sl.partial = cv.take<uint32_t>(size_t(16) * slot_grid);
+    sl.ss = cv.take<SlotState>(1);
+    sl.arena_cap = uint32_t(arena_cap);
+    sl.chunk_cap = uint32_t(chunk_cap);
+    sl.dir_cap = uint32_t(dir_cap);
+    H->slot_grid = slot_grid;
+  }
   if (!cv.ok()) { set_error(c, "cse_begin: scratch carve failed (need %zu)", need); return BCE_GPU_E_NOMEM; }
   H->ecap_words = ew;
   // per-stream target: the streams are uneven (the largest carries about a third of the words), so a third of the
@@ -799,11 +863,33 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
       BCE_CUDA(c, cudaGetLastError());
     } else {
       // 1024-node tiles while the frontier is huge, 512-node tiles below (more CTAs per round)
-      constexpr unsigned long long kBig = 2000000, kLeaveBig = 1000000, kLeaveSmall = 3000000;
+      const unsigned long long kBig = c->slot_enter_nodes, kLeaveBig = kBig / 2, kLeaveSmall = kBig + kBig / 2;
       H->args.min_nodes = 0;
       H->args.max_nodes = ~0ull;
       int v;
       int grid;
+      const bool use_slots = H->slots_ok && (H->in_slots || H->known_nodes >= kBig);
+      if (use_slots) {
+        // huge frontier: slot layout.  Coming from the flat layout it is converted first and the kernel starts with its
+        // scan phase; it comes back (kCseGoWide) when fewer than kLeaveBig nodes are left.
+        grid = H->slot_grid;
+        H->args.min_nodes = kLeaveBig;
+        if (grid != H->last_grid) {
+          if (H->last_grid) { cse_reset_barrier_kernel<<<1, 1, 0, st>>>(H->args.st); c->stats.gpu_launches++; }
+          H->last_grid = grid;
+        }
+        uint32_t first_scan = 0;
+        if (!H->in_slots) {
+          cse_flat_to_slots_kernel<<<c->sm_count * 4, 256, 0, st>>>(H->args, H->slot);
+          c->stats.gpu_launches++;
+          BCE_CUDA(c, cudaGetLastError());
+          first_scan = 1;
+          H->in_slots = true;
+        }
+        void* kargs[] = {&H->args, &H->slot, &first_scan};
+        BCE_CUDA(c, cudaLaunchCooperativeKernel(H->slot_fn, dim3(grid), dim3(SL_THREADS), kargs, 0, st));
+        v = -1;
+      } else
       if (H->fixed_items) { v = H->fixed_items == 4 ? 1 : 0; grid = H->var_grid[v]; }
       else {
         v = H->known_nodes >= kBig ? 1 : 0;
@@ -821,6 +907,7 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
           }
         }
       }
+      if (v >= 0) {
       if (grid != H->last_grid) {
         if (H->last_grid) { cse_reset_barrier_kernel<<<1, 1, 0, st>>>(H->args.st); c->stats.gpu_launches++; }
         H->last_grid = grid;
@@ -829,9 +916,21 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
         BCE_CUDA(c, cudaMemsetAsync(H->args.desc, 0, 3 * size_t(H->args.desc_tiles) * sizeof(uint64_t), st));
         H->desc_epoch = H->last_round >> 29;
       }
+#ifdef BCE_GPU_EXPERIMENTS
+      if (H->args.dbg & (8u | 16u | 32u)) {           // independent-warp probe of this round (packed emission only)
+        const int ctas = int(env_size("BCE_GPU_PROBE_CTAS", 0));
+        if (H->args.dbg & 8u) cse_slot_probe_kernel<1, 6><<<c->sm_count * (ctas ? ctas : 6), 256, 0, st>>>(H->args);
+        else if (H->args.dbg & 16u) cse_slot_probe_kernel<2, 4><<<c->sm_count * (ctas ? ctas : 4), 256, 0, st>>>(H->args);
+        else cse_slot_probe_kernel<4, 3><<<c->sm_count * (ctas ? ctas : 3), 256, 0, st>>>(H->args);
+      } else {
+#endif
       void* kargs[] = {&H->args};
       BCE_CUDA(c, cudaLaunchCooperativeKernel(H->var_fn[v], dim3(grid), dim3(CS_THREADS), kargs,
                                               H->var_smem[v], st));
+#ifdef BCE_GPU_EXPERIMENTS
+      }
+#endif
+      }
     }
     c->stats.gpu_launches++;
     c->stats.cse_launches++;
@@ -842,10 +941,19 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
       float lms = 0;
       BCE_CUDA(c, cudaEventElapsedTime(&lms, c->ev[0], c->ev[1]));
       if (was_narrow) { c->stats.ms_cse_narrow += lms; c->stats.cse_rounds_narrow += h_state->round - H->last_round; }
-      BCE_TRACE("cse %s kernel: rounds %u..%u status=%u err=%u visits=%llu %.3f ms dbg=%u", was_narrow ? "narrow" : "wide",
+      BCE_TRACE("cse %s kernel: rounds %u..%u status=%u err=%u visits=%llu %.3f ms dbg=%u", was_narrow ? "narrow" : H->in_slots ? "slots" : "wide",
                 H->last_round, h_state->round, h_state->status, h_state->err, h_state->visits, lms, H->args.dbg);
       if (H->args.dbg) { set_error(c, "cse: timing experiment round done (%.3f ms)", lms); return BCE_GPU_E_INTERNAL; }
       H->last_round = h_state->round;
+      if (H->in_slots && h_state->status == kCseGoWide && !h_state->err) {
+        // the frontier has shrunk: back to the flat layout (exact half sizes come with it)
+        cse_slots_to_flat_kernel<<<c->sm_count * 4, 256, 0, st>>>(H->args, H->slot);
+        c->stats.gpu_launches++;
+        BCE_CUDA(c, cudaGetLastError());
+        BCE_CUDA(c, cudaMemcpyAsync(h_state, H->args.st, sizeof(CseDeviceState), cudaMemcpyDeviceToHost, st));
+        BCE_CUDA(c, cudaStreamSynchronize(st));
+        H->in_slots = false;
+      }
       const int par = h_state->round & 1;
       H->known_nodes = 0;
       for (int l = 0; l < 8; ++l) H->known_nodes += h_state->cnt[par][l][0] + h_state->cnt[par][l][1];

@@ -43,7 +43,7 @@ struct WideStage {                                  // one staging buffer
 };
 
 template <int ITEMS, int EW>
-__global__ void __launch_bounds__(CS_THREADS, 2) cse_wide_kernel(CseArgs a) {
+__global__ void __launch_bounds__(CS_THREADS, 512 / CS_THREADS) cse_wide_kernel(CseArgs a) {
   constexpr int TILE = CS_THREADS * ITEMS;
   extern __shared__ __align__(16) unsigned char wide_smem[];
   WideStage<ITEMS, EW>* stage = reinterpret_cast<WideStage<ITEMS, EW>*>(wide_smem);   // [2]

@@ -57,6 +57,7 @@ struct Ctx : bce_gpu_ctx {
   size_t emit_batch_bytes = size_t(1) << 30;   // BCE_GPU_OPT_EMIT_BATCH_BYTES
   uint32_t local_sort_min = 1u << 20;          // BCE_GPU_OPT_LOCAL_SORT_MIN
   bool resident_checksum = false;              // BCE_GPU_OPT_RESIDENT_CHECKSUM
+  uint64_t slot_enter_nodes = 2000000;         // BCE_GPU_OPT_SLOT_ENTER_NODES
 
   // state of the current input
   uint32_t n = 0;

@@ -375,6 +375,72 @@ __global__ void __launch_bounds__(256) bwt_gather_kernel(const uint8_t* __restri
   else for (int j = 0; r4 + j < n; ++j) L[r4 + j] = uint8_t(out >> (8 * j));
 }
 
+// The same through the inverse: after the last round rnk[i] is the SA row of rotation i, so L[rnk[i]] = T[i - 1].
+// A one-byte store per row to a random address costs a DRAM sector each way (ncu, round 1: 39 B per row, 69 % DRAM
+// busy, 19 ms at 1 GB).  Here the rows are binned first: K5a reads rnk and T as streams and writes (row inside its bin
+// << 8 | byte) grouped by the row's top bits -- a counting sort of the tile in shared memory, one atomicAdd per
+// (tile, bin) on the bin's cursor, one run per bin; the order inside a bin is irrelevant, every word is a store to its
+// own address, and the bin sizes are arithmetic because rnk is a permutation -- and K5b stores from that order, so a
+// bin's slice of L (n / 256 bytes) is filled while it sits in L2.  5 + 4 + 4 + 1 = 14 B per row of streams.
+constexpr int BG_THREADS = 256, BG_ITEMS = 16, BG_TILE = BG_THREADS * BG_ITEMS;
+__global__ void bwt_cursor_kernel(uint32_t* cursor, int shift) { cursor[threadIdx.x] = threadIdx.x << shift; }
+
+__global__ void __launch_bounds__(BG_THREADS) bwt_bin_kernel(const uint8_t* __restrict__ T, const uint32_t* __restrict__ rnk,
+                                                             uint32_t n, int shift, uint32_t* __restrict__ cursor,
+                                                             uint32_t* __restrict__ pairs) {
+  __shared__ uint32_t s_cnt[256], s_start[256], s_gbase[256];
+  __shared__ uint32_t s_scan[BG_THREADS / 32];
+  __shared__ uint32_t s_stage[BG_TILE];
+  __shared__ uint8_t s_bin[BG_TILE];
+  const unsigned tid = threadIdx.x;
+  const uint32_t base = blockIdx.x * BG_TILE;
+  s_cnt[tid] = 0;
+  __syncthreads();
+  uint32_t word[BG_ITEMS], pos[BG_ITEMS];
+  const uint32_t mask = (1u << shift) - 1u;
+#pragma unroll
+  for (int k = 0; k < BG_ITEMS; ++k) {
+    const uint32_t i = base + k * BG_THREADS + tid;
+    word[k] = pos[k] = 0;
+    if (i < n) {
+      const uint32_t r = rnk[i];
+      const uint32_t byte = T[i ? i - 1 : n - 1];
+      const uint32_t bin = r >> shift;
+      pos[k] = atomicAdd(&s_cnt[bin], 1u) | (bin << 16);         // place inside the tile's bin (any order will do); BG_TILE <= 65536
+      word[k] = ((r & mask) << 8) | byte;
+    }
+  }
+  __syncthreads();
+  uint32_t tot;
+  const uint32_t mine = s_cnt[tid];
+  s_start[tid] = block_exclusive_scan<uint32_t, BG_THREADS>(mine, s_scan, tot);
+  if (mine) s_gbase[tid] = atomicAdd(&cursor[tid], mine);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < BG_ITEMS; ++k)
+    if (base + k * BG_THREADS + tid < n) {
+      const uint32_t at = s_start[pos[k] >> 16] + (pos[k] & 0xFFFFu);
+      s_stage[at] = word[k];
+      s_bin[at] = uint8_t(pos[k] >> 16);
+    }
+  __syncthreads();
+  const uint32_t valid = min(uint32_t(BG_TILE), n - base);
+  for (uint32_t j = tid; j < valid; j += BG_THREADS) {          // one run per bin
+    const uint32_t bin = s_bin[j];
+    pairs[s_gbase[bin] + (j - s_start[bin])] = s_stage[j];
+  }
+}
+
+// rnk is a permutation of the rows, so bin b holds exactly the rows [b << shift, (b + 1) << shift) and its words sit
+// at those positions of `pairs`
+__global__ void __launch_bounds__(256) bwt_scatter_kernel(const uint32_t* __restrict__ pairs, uint32_t n, int shift,
+                                                          uint8_t* __restrict__ L) {
+  for (uint32_t j = blockIdx.x * 256u + threadIdx.x; j < n; j += gridDim.x * 256u) {
+    const uint32_t p = pairs[j];
+    L[((j >> shift) << shift) + (p >> 8)] = uint8_t(p);
+  }
+}
+
 static inline int bits_for(uint32_t values) {   // bits needed for 0 .. values-1
   int b = 0;
   while (b < 32 && (uint64_t(1) << b) < values) ++b;
@@ -465,6 +531,7 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
   uint32_t m = n, groups = 0;
   uint64_t h = 8;
   const int nbits = bits_for(n);
+  bool had_tiebreak = false;              // identical rotations were ordered by index: rnk is then not a permutation
 
   for (int round = 0;; ++round) {
     if (round >= kMaxSortRounds) { set_error(c, "suffix sort: too many rounds"); return BCE_GPU_E_INTERNAL; }
@@ -480,6 +547,7 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
       for (int s = 0; s < 64; s += 8) shifts[np++] = s;
     } else {
       tiebreak = h >= n;
+      if (tiebreak) had_tiebreak = true;
       for (int s = 0; s < nbits; s += 8) shifts[np++] = s;
       int gbits = bits_for(groups);
       for (int s = 0; s < gbits && np < 8; s += 8) shifts[np++] = 32 + s;
@@ -661,8 +729,19 @@ int suffix_sort_bwt(Ctx* c, uint32_t n, uint32_t* sa_host) {
     if (round == 0) h = 8;
   }
 
-  bwt_gather_kernel<<<((n + 3) / 4 + 255) / 256, 256, 0, st>>>(T, sa, n, L);
-  S.gpu_launches++;
+  // binned inverse form for inputs whose T does not fit L2 anyway; needs rnk to be the inverse suffix array, which it
+  // is unless identical rotations were told apart by index (then equal rotations share a rank)
+  if (!had_tiebreak && n >= (8u << 20) && exp_env("BCE_GPU_BWT_GATHER", 0) == 0) {
+    const int shift = std::max(0, bits_for(n) - 8);
+    uint32_t* pairs = reinterpret_cast<uint32_t*>(keyA);             // the sort's buffers are dead
+    bwt_cursor_kernel<<<1, 256, 0, st>>>(d_pcursor, shift);
+    bwt_bin_kernel<<<(n + BG_TILE - 1) / BG_TILE, BG_THREADS, 0, st>>>(T, rnk, n, shift, d_pcursor, pairs);
+    bwt_scatter_kernel<<<(n + 255) / 256, 256, 0, st>>>(pairs, n, shift, L);
+    S.gpu_launches += 3;
+  } else {
+    bwt_gather_kernel<<<((n + 3) / 4 + 255) / 256, 256, 0, st>>>(T, sa, n, L);
+    S.gpu_launches++;
+  }
   BCE_CUDA(c, cudaGetLastError());
   BCE_CUDA(c, cudaMemcpyAsync(h_small, sa, 4, cudaMemcpyDeviceToHost, st));
   BCE_TRY(lap(S.ms_bwt_gather));

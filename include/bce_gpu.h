@@ -103,8 +103,11 @@ int bce_gpu_set_scratch_limit(bce_gpu_ctx *ctx, size_t bytes);
  *                     1 GiB; small values force many batches -- used by the tests of the draining path)
  *   LOCAL_SORT_MIN    working sets of the suffix sort below this many rotations take the plain
  *                     radix path instead of the tile-local sort (default 2^20)
- *   RESIDENT_CHECKSUM 1 = front_resident also sums the words it emits (see bce_gpu_resident_checksum) */
-enum { BCE_GPU_OPT_EMIT_BATCH_BYTES = 1, BCE_GPU_OPT_LOCAL_SORT_MIN = 2, BCE_GPU_OPT_RESIDENT_CHECKSUM = 3 };
+ *   RESIDENT_CHECKSUM 1 = front_resident also sums the words it emits (see bce_gpu_resident_checksum)
+ *   SLOT_ENTER_NODES  the level loop keeps frontiers of at least this many nodes per round in its slot layout
+ *                     (default 2,000,000; inputs below 8x this never use it; small values: tests) */
+enum { BCE_GPU_OPT_EMIT_BATCH_BYTES = 1, BCE_GPU_OPT_LOCAL_SORT_MIN = 2, BCE_GPU_OPT_RESIDENT_CHECKSUM = 3,
+       BCE_GPU_OPT_SLOT_ENTER_NODES = 4 };
 int bce_gpu_set_option(bce_gpu_ctx *ctx, int option, uint64_t value);
 
 /* ---- stage A: suffix sort / BWT ------------------------------------------------

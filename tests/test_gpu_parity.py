@@ -129,6 +129,41 @@ def test_resident_matches_hosted(frontend):
         frontend.set_option(OPT_RESIDENT_CHECKSUM, 0)
 
 
+def test_slot_layout_forced_on_small_inputs(frontend):
+    """Frontiers of millions of nodes per round live in the slot layout (csrc/cse_slots.cuh): per-chunk output slots, a
+    scan of the slot counts between rounds, conversion from and back to the flat layout.  That only switches on at
+    sizes the oracle cannot check, so it is forced here on everything from 16 K bytes up: every count of every stream
+    (raw), the packed words' archive, and several small batches (the kernel stops to drain while in slots)."""
+    from bce_b200.gpu import OPT_EMIT_BATCH_BYTES, OPT_SLOT_ENTER_NODES
+    frontend.set_option(OPT_SLOT_ENTER_NODES, 2048)
+    try:
+        used = 0
+        for name, data, _ in small_cases() + medium_cases():
+            if len(data) < 8 * 2048:
+                continue
+            Lo, offo, _ = oracle.bwt(data)
+            want = oracle.cse(oracle.wavelet(Lo), len(data))
+            off, Cv, streams = frontend.compress_front(data)
+            st = frontend.stats()
+            assert off == offo and Cv == want["C"], name
+            for i in range(8):
+                assert first_diff(streams[i], want["streams"][i]) is None, (name, i)
+            assert st["cse_visits"] == sum(want["visits"]) and st["cse_rounds"] == want["rounds"], name
+            assert host.compress(frontend, data, threads=1) == oracle.compress(data), name
+            frontend.set_option(OPT_EMIT_BATCH_BYTES, 1 << 20)
+            try:
+                _, streams2 = frontend.cse(Lo)
+                assert frontend.last_batches > 1
+            finally:
+                frontend.set_option(OPT_EMIT_BATCH_BYTES, 0)
+            for i in range(8):
+                assert first_diff(streams2[i], want["streams"][i]) is None, (name, i, "batched")
+            used += 1
+        assert used >= 5
+    finally:
+        frontend.set_option(OPT_SLOT_ENTER_NODES, 0)
+
+
 def test_scan_buckets_from_the_device(frontend):
     """bce_gpu_cse_next_buckets: per stream and (k, key) the device's runs of symbol bytes, joined over
     the batches, are the stream's SCAN words of that bucket in order; keys first appear in stream order; the

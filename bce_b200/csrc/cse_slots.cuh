@@ -24,9 +24,12 @@
 
 namespace bce {
 
-constexpr int SL_ITEMS = 2;                       // nodes per lane: 56 registers, 4 CTAs per SM (probe: as fast as 4 per lane at 3)
+#ifndef BCE_SL_ITEMS
+#define BCE_SL_ITEMS 4
+#endif
+constexpr int SL_ITEMS = BCE_SL_ITEMS;            // nodes per lane: 4 = 78 registers, 3 CTAs/SM (1 GB: 101 ms); 2 = 64 registers, 4 CTAs/SM (109 ms)
 constexpr uint32_t SL_CH = 32 * SL_ITEMS;         // nodes per chunk = places per slot
-constexpr int SL_THREADS = 256, SL_WARPS = SL_THREADS / 32, SL_MINB = 4;
+constexpr int SL_THREADS = 256, SL_WARPS = SL_THREADS / 32, SL_MINB = SL_ITEMS <= 2 ? 4 : 3;
 
 struct SlotLevel {               // one level's frontier in slot form
   uint32_t n;                    // nodes
@@ -219,11 +222,37 @@ __global__ void __launch_bounds__(SL_THREADS, SL_MINB) cse_slots_kernel(CseArgs 
     if (!scan_only) {
       if (blockIdx.x == 0 && tid < 8) SS->lv[nxt][tid] = s_nxt[tid];   // n is filled in by phase B
       // ================= phase A: every warp on its own ============================================================
-      for (uint32_t t = blockIdx.x * SL_WARPS + warp; t < total_chunks; t += G * SL_WARPS) {
-        int l = 0;
-#pragma unroll
-        for (int i = 1; i < 8; ++i)
-          if (t >= s_tfirst[i]) l = i;
+      // The chunk's place in the slots comes from two dependent loads (start[q], then the P window behind it) before
+      // its nodes can even be asked for: both are fetched one / two chunks ahead, so that the chain a warp waits for is
+      // nodes -> rank words only.
+      const uint32_t stride = G * SL_WARPS;
+      auto level_of = [&](uint32_t t) {                   // 3 compares: s_tfirst ascends
+        int l = t >= s_tfirst[4] ? 4 : 0;
+        l += t >= s_tfirst[l + 2] ? 2 : 0;
+        l += t >= s_tfirst[l + 1] ? 1 : 0;
+        return l;
+      };
+      auto load_start = [&](uint32_t t, int l) -> uint32_t {
+        return t < total_chunks ? sa.start[cur][s_cur[l].soff + (t - s_tfirst[l])] : 0u;
+      };
+      auto load_window = [&](uint32_t t, int l, uint32_t base, uint32_t& p0, uint32_t& pw) {
+        p0 = 0; pw = 0xFFFFFFFFu;
+        if (t >= total_chunks) return;
+        const uint32_t* __restrict__ P = sa.P[cur] + s_cur[l].doff + l;
+        const uint32_t e = base + 1u + lane;
+        p0 = P[base];
+        if (e <= s_cur[l].sz + s_cur[l].so) pw = P[e];
+      };
+      uint32_t t = blockIdx.x * SL_WARPS + warp;
+      int l = level_of(min(t, total_chunks - 1u)), l1 = level_of(min(t + stride, total_chunks - 1u));
+      uint32_t cu_base = load_start(t, l), cu_p0, cu_pw;
+      load_window(t, l, cu_base, cu_p0, cu_pw);
+      uint32_t nx_base = load_start(t + stride, l1);
+      for (; t < total_chunks; t += stride) {
+        uint32_t n_p0, n_pw;
+        load_window(t + stride, l1, nx_base, n_p0, n_pw);               // next chunk: its start arrived an iteration ago
+        const int l2 = level_of(min(t + 2u * stride, total_chunks - 1u));
+        const uint32_t nn_base = load_start(t + 2u * stride, l2);       // the one after: start only
         const int ln = (l + 1) & 7;
         const uint32_t q = t - s_tfirst[l];
         const SlotLevel v = s_cur[l];
@@ -232,15 +261,11 @@ __global__ void __launch_bounds__(SL_THREADS, SL_MINB) cse_slots_kernel(CseArgs 
         const uint32_t* __restrict__ P = sa.P[cur] + v.doff + l;
         // --- where the chunk's nodes are: slot c and offset inside it for every position
         uint32_t c[SL_ITEMS], pc[SL_ITEMS], g[SL_ITEMS];
-        uint32_t base = sa.start[cur][v.soff + q];
-        {
-          const uint32_t p0 = P[base];
+        uint32_t base = cu_base;
 #pragma unroll
-          for (int j = 0; j < SL_ITEMS; ++j) { g[j] = gbase + 32u * j + lane; c[j] = base; pc[j] = p0; }
-        }
+        for (int j = 0; j < SL_ITEMS; ++j) { g[j] = gbase + 32u * j + lane; c[j] = base; pc[j] = cu_p0; }
+        uint32_t pwv = cu_pw;
         for (;;) {                                                      // windows of 32 following slots (one is the rule)
-          const uint32_t e = base + 1u + lane;
-          const uint32_t pwv = e <= slots ? P[e] : 0xFFFFFFFFu;
           const unsigned le = __ballot_sync(0xffffffffu, pwv < gend);   // slots that start inside the chunk
           const int nle = __popc(le);                                   // P ascends: they are the first nle lanes
           for (int i = 0; i < nle; ++i) {
@@ -251,7 +276,10 @@ __global__ void __launch_bounds__(SL_THREADS, SL_MINB) cse_slots_kernel(CseArgs 
           }
           if (nle < 32) break;
           base += 32u;
+          const uint32_t e = base + 1u + lane;
+          pwv = e <= slots ? P[e] : 0xFFFFFFFFu;
         }
+        cu_base = nx_base; cu_p0 = n_p0; cu_pw = n_pw; nx_base = nn_base;
         // --- nodes and their three rank words
         uint32_t ns[SL_ITEMS], na[SL_ITEMS], nb[SL_ITEMS];
         uint64_t wa[SL_ITEMS], wb[SL_ITEMS], wc[SL_ITEMS];
@@ -332,6 +360,7 @@ __global__ void __launch_bounds__(SL_THREADS, SL_MINB) cse_slots_kernel(CseArgs 
           sa.cnt[nxt][nv.doff + nv.sz + q] = uint8_t(co);
           sa.ecnt[t] = uint16_t(ce);
         }
+        l = l1; l1 = l2;
       }
       grid_barrier(S, barrier_no++, round);
     }

@@ -292,6 +292,25 @@ int bce_gpu_set_scratch_limit(bce_gpu_ctx* h, size_t bytes) {
   return BCE_GPU_OK;
 }
 
+void* bce_gpu_host_alloc(bce_gpu_ctx* h, size_t bytes) {
+  if (!h || !bytes) return nullptr;
+  Ctx* c = static_cast<Ctx*>(h);
+  cudaSetDevice(c->device);
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    bce::set_error(c, "cudaHostAlloc(%zu bytes) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+void bce_gpu_host_free(bce_gpu_ctx* h, void* p) {
+  if (!h || !p) return;
+  cudaSetDevice(static_cast<Ctx*>(h)->device);
+  cudaFreeHost(p);
+}
+
 int bce_gpu_set_option(bce_gpu_ctx* h, int option, uint64_t value) {
   if (!h) return BCE_GPU_E_ARG;
   Ctx* c = static_cast<Ctx*>(h);

@@ -26,22 +26,44 @@
 
 namespace {
 
-bool slurp(const std::string& path, std::vector<uint8_t>& out) {        // File::File, bce.cpp:842-856
-  std::ifstream f(path, std::ios::binary | std::ios::ate);
-  if (!f) return false;
-  const std::streamoff size = f.tellg();
-  if (size < 0) return false;
-  out.resize(size_t(size));
-  f.seekg(0, std::ios::beg);
-  return size == 0 || bool(f.read(reinterpret_cast<char*>(out.data()), size));
-}
+// File::File, bce.cpp:842-856: the whole file in one buffer -- page-locked here, so that the upload to the
+// device is one DMA transfer straight out of it (pageable memory would go through staged copies).
+struct InputFile {
+  bce_gpu_ctx* ctx = nullptr;
+  uint8_t* data = nullptr;
+  size_t size = 0;
+  bool pinned = false;
+  ~InputFile() { release(); }
+  void release() {
+    if (data) { if (pinned) bce_gpu_host_free(ctx, data); else std::free(data); }
+    data = nullptr;
+  }
+  // 0 = ok, 1 = cannot read / empty, 2 = too large for the format
+  int load(const std::string& path, bce_gpu_ctx* c) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) return 1;
+    const std::streamoff sz = f.tellg();
+    if (sz <= 0) return 1;
+    // the format carries n as a varint of at most 31 binary digits (bce.cpp:372-377) and every index is a uint32:
+    // the reference silently wraps on larger files, this tool refuses them
+    if (uint64_t(sz) > 0x7FFFFFFFull) {
+      std::printf("File too large: %" PRIuMAX " B (the BCE v0.4 format holds at most 2147483647 B)\n", uintmax_t(sz));
+      return 2;
+    }
+    ctx = c;
+    size = size_t(sz);
+    data = c ? static_cast<uint8_t*>(bce_gpu_host_alloc(c, size)) : nullptr;
+    pinned = data != nullptr;
+    if (!data) data = static_cast<uint8_t*>(std::malloc(size));
+    if (!data) return 1;
+    f.seekg(0, std::ios::beg);
+    return f.read(reinterpret_cast<char*>(data), sz) ? 0 : 1;
+  }
+};
 
-// The format carries n as a varint of at most 31 binary digits (bce.cpp:372-377) and every index is a
-// uint32: the reference silently wraps on larger files, this tool refuses them.
-bool too_large(const std::vector<uint8_t>& data) {
-  if (data.size() <= 0x7FFFFFFFull) return false;
-  std::printf("File too large: %" PRIuMAX " B (the BCE v0.4 format holds at most 2147483647 B)\n", uintmax_t(data.size()));
-  return true;
+bool exists_nonempty(const std::string& path) {
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  return f && f.tellg() > 0;
 }
 
 int gpu_failure(bce_gpu_ctx* ctx, int rc) {
@@ -72,24 +94,31 @@ int main(int argc, char** argv) {
 
   if (argc == 4 && flag && argv[1][1] == 's') {                          // bce.cpp:1384-1402
     const auto start = clock::now();
-    std::vector<uint8_t> data;
-    if (!slurp(argv[3], data) || data.empty()) {
+    if (!exists_nonempty(argv[3])) {                                     // before the device is touched (:1390-1393)
       std::printf("Error loading file\n");
       return -1;
     }
-    if (too_large(data)) return -1;
     bce_gpu_ctx* ctx = nullptr;
     int rc = bce_gpu_open(0, &ctx);
     if (rc) return gpu_failure(ctx, rc);
+    InputFile data;
+    if (int lr = data.load(argv[3], ctx)) {
+      if (lr == 1) std::printf("Error loading file\n");
+      data.release();
+      bce_gpu_close(ctx);
+      return -1;
+    }
     uint8_t cfg[288];
-    rc = bce_scan_buffer(ctx, data.data(), uint32_t(data.size()), cfg);
-    if (rc) { gpu_failure(ctx, rc); bce_gpu_close(ctx); return rc; }
+    rc = bce_scan_buffer(ctx, data.data, uint32_t(data.size), cfg);
+    if (rc) { gpu_failure(ctx, rc); data.release(); bce_gpu_close(ctx); return rc; }
+    const size_t scanned = data.size;
+    data.release();
     bce_gpu_close(ctx);
     bcehost::ConfigTable table;
     std::memcpy(table.data(), cfg, 288);
     bcehost::save_config_file(argv[2], table);
     const std::chrono::duration<double> d = clock::now() - start;
-    std::printf("Scanned %" PRIuMAX " B in %.1f s\n", uintmax_t(data.size()), d.count());
+    std::printf("Scanned %" PRIuMAX " B in %.1f s\n", uintmax_t(scanned), d.count());
     return 0;
   }
 
@@ -97,27 +126,32 @@ int main(int argc, char** argv) {
     const auto start = clock::now();
     bcehost::ConfigTable table = bcehost::default_config();
     if (argc == 5) bcehost::load_config_file(argv[4], table);            // failure is non-fatal (:629-632)
-    std::vector<uint8_t> data;
-    if (!slurp(argv[3], data) || data.empty()) {
+    if (!exists_nonempty(argv[3])) {                                     // before the device is touched (:1412-1415)
       std::printf("Error loading file\n");
       return -1;
     }
-    if (too_large(data)) return -1;
     const bool timing = std::getenv("BCE_TIME") != nullptr;
-    const auto t_read = clock::now();
     bce_gpu_ctx* ctx = nullptr;
     int rc = bce_gpu_open(0, &ctx);
     if (rc) return gpu_failure(ctx, rc);
+    const auto t_open = clock::now();
+    InputFile data;
+    if (int lr = data.load(argv[3], ctx)) {
+      if (lr == 1) std::printf("Error loading file\n");
+      data.release();
+      bce_gpu_close(ctx);
+      return -1;
+    }
     if (timing)
-      std::fprintf(stderr, "[bce] read %.3f s | open device %.3f s\n", std::chrono::duration<double>(t_read - start).count(),
-                   std::chrono::duration<double>(clock::now() - t_read).count());
+      std::fprintf(stderr, "[bce] open device %.3f s | read into page-locked memory %.3f s\n",
+                   std::chrono::duration<double>(t_open - start).count(), std::chrono::duration<double>(clock::now() - t_open).count());
     uint16_t* words = nullptr;
     size_t nwords = 0;
-    rc = bce_compress_buffer(ctx, data.data(), uint32_t(data.size()),
+    rc = bce_compress_buffer(ctx, data.data, uint32_t(data.size),
                              reinterpret_cast<const uint8_t*>(table.data()), 8, &words, &nwords);
-    if (rc) { gpu_failure(ctx, rc); bce_gpu_close(ctx); return rc; }
+    if (rc) { gpu_failure(ctx, rc); data.release(); bce_gpu_close(ctx); return rc; }
     const std::chrono::duration<double> d = clock::now() - start;
-    std::printf("Compressed from %" PRIuMAX " B -> %zu B in %.1f s\n", uintmax_t(data.size()),
+    std::printf("Compressed from %" PRIuMAX " B -> %zu B in %.1f s\n", uintmax_t(data.size),
                 nwords * sizeof(uint16_t), d.count());
     const auto t_write = clock::now();
     {
@@ -132,6 +166,7 @@ int main(int argc, char** argv) {
     // (BCE_CLEAN_EXIT=1 keeps the orderly teardown for leak checkers).
     if (std::getenv("BCE_CLEAN_EXIT")) {
       bce_host_free(words);
+      data.release();
       bce_gpu_close(ctx);
       return 0;
     }

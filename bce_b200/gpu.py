@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "bce_gpu_wavelet", "bce_gpu_cse_begin", "bce_gpu_cse_next", "bce_gpu_compress_front",
     "bce_gpu_stage_input", "bce_gpu_front_resident", "bce_gpu_unbwt",
     "bce_gpu_set_emit_mode", "bce_gpu_cse_next_words", "bce_gpu_set_option",
-    "bce_gpu_resident_checksum", "bce_gpu_cse_next_buckets",
+    "bce_gpu_resident_checksum", "bce_gpu_cse_next_buckets", "bce_gpu_host_alloc", "bce_gpu_host_free",
 ]
 OPT_EMIT_BATCH_BYTES, OPT_LOCAL_SORT_MIN, OPT_RESIDENT_CHECKSUM, OPT_SLOT_ENTER_NODES = 1, 2, 3, 4
 
@@ -114,6 +114,9 @@ def load_library() -> C.CDLL:
     lib.bce_gpu_set_scratch_limit.argtypes = [vp, C.c_size_t]
     lib.bce_gpu_set_option.argtypes = [vp, C.c_int, C.c_uint64]
     lib.bce_gpu_cse_next_buckets.argtypes = [vp, C.POINTER(ScanBuckets)]
+    lib.bce_gpu_host_alloc.argtypes = [vp, C.c_size_t]
+    lib.bce_gpu_host_alloc.restype = vp
+    lib.bce_gpu_host_free.argtypes = [vp, vp]
     lib.bce_gpu_resident_checksum.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.bce_gpu_bwt.argtypes = [vp, vp, u32, vp, u32p, vp]
     lib.bce_gpu_wavelet.argtypes = [vp, vp, u32, C.POINTER(vp), u32p]

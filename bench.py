@@ -215,6 +215,93 @@ def algorithmic_bytes(st: dict, executed: bool = False) -> dict:
     return {"stage_a": stage_a, "stage_b": stage_b, "total": stage_a + stage_b}
 
 
+def run_batch_workload(args, rank: int, world: int, local_rank: int):
+    """configs[4]: 64 files of 128 MiB (the enwik-shaped generator, seeds 100..163), one archive per file, on N GPUs.
+    A step is the whole batch through bce_b200.batch.compress_files: workers pull files from a shared queue, read
+    them, run the GPU front end + host range coders, write <file>.bce.  Untimed: generating the files.  `value` is
+    the GPU-stage throughput (all bytes / the busiest rank's summed front-end time), `e2e` the true `bce -c` rate
+    of the batch (wall clock of the slowest rank, file read and archive write included)."""
+    import hashlib
+    import shutil
+    import tempfile
+
+    import torch
+    import torch.distributed as dist
+
+    from bce_b200 import batch, synth
+    torch.cuda.set_device(local_rank)
+    gen, nbytes, seed0 = WORKLOADS["batch-128MB"]
+    nfiles = args.files
+    root = Path(os.environ.get("BCE_BENCH_TMP", "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir())) / "bce_batch_bench"
+    if rank == 0:
+        shutil.rmtree(root, ignore_errors=True)
+        (root / "in").mkdir(parents=True)
+    if world > 1:
+        dist.barrier()
+    for i in range(rank, nfiles, world):                       # untimed: synthetic inputs
+        synth.generate(gen, nbytes, seed0 + i).tofile(root / "in" / f"file{i:02d}")
+    if world > 1:
+        dist.barrier()
+    paths = [str(root / "in" / f"file{i:02d}") for i in range(nfiles)]
+    # files in flight per GPU: a file's front end takes a tenth of the time its 8 coder threads do
+    in_flight = args.in_flight or max(1, min(2, (os.cpu_count() or 8) // (8 * world)))
+    fns = [batch.make_gpu_compressor(local_rank) for _ in range(in_flight)]
+    for f in fns:
+        f(synth.generate(gen, 1 << 22, 1), None)                # warm-up: context, buffers, kernels
+    sampler = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    res = batch.compress_files(paths, str(root / "out"), fns, device="cuda" if world > 1 else "cpu")
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = sum(f.gpu_launches for f in fns)
+    if world > 1:
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+        t = torch.tensor([launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        launches = int(t.item())
+    if rank == 0:
+        tot = res.total
+        golden = {}
+        try:
+            vec = json.loads((ROOT / "tests" / "golden" / "big_vectors.json").read_text())["vectors"]
+            for name, idx in (("batch-128MB-seed100", 0), ("batch-128MB-seed163", 63)):
+                f = root / "out" / f"file{idx:02d}.bce"
+                if name in vec and f.exists():
+                    golden[name] = hashlib.sha256(f.read_bytes()).hexdigest() == vec[name]["archive_sha256"]
+        except Exception as e:                                   # noqa: BLE001
+            golden = {"error": str(e)}
+        gpu_s = tot.gpu_ms / 1e3
+        line = {
+            "metric": METRIC, "value": tot.bytes_in / gpu_s / 1e6 if gpu_s else None, "unit": UNIT, "n_gpus": world,
+            "steps": 1, "warmup": 1, "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
+            "config": {"workload": "batch-128MB", "generator": gen, "files": nfiles, "bytes_per_file": nbytes,
+                       "seeds": [seed0, seed0 + nfiles - 1], "files_in_flight_per_gpu": in_flight,
+                       "parallelism": f"replicas x{world}, shared file queue",
+                       "l2": "every file's working set exceeds L2; no flush"},
+            "e2e": {"value": tot.bytes_in / wall / 1e6, "unit": UNIT, "what": "files read, compressed (GPU front end + host "
+                    "coders, 8 threads per in-flight file) and written as .bce; wall clock of the slowest rank",
+                    "h2d_bytes_per_step": tot.bytes_in, "d2h_bytes_per_step": None, "archives_per_s": tot.inputs / wall},
+            "batch": {"files_ok": tot.inputs, "files_failed": tot.failed, "bytes_in": tot.bytes_in, "bytes_out": tot.bytes_out,
+                      "wall_s": wall, "gpu_s_busiest_rank": gpu_s,
+                      "per_rank": [vars(r) for r in res.per_rank],
+                      "files_per_rank": [sum(1 for f in res.files if f.rank == r) for r in range(world)],
+                      "archives_equal_reference": golden, "host_cores": os.cpu_count()},
+            "gpu_launches": launches, "clocks": clocks, "native_note": NATIVE_NOTE,
+        }
+        print(json.dumps(line))
+        shutil.rmtree(root, ignore_errors=True)
+    for f in fns:
+        f.frontend.close()
+    return 0
+
+
 def run_ours(args, rank: int, world: int, local_rank: int):
     import numpy as np
     import torch
@@ -430,6 +517,9 @@ def main():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--bytes", type=int, default=0, help="override the input size (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--files", type=int, default=64, help="--workload batch-128MB: files in the batch (0 = time one "
+                    "128 MiB input per GPU like the other workloads)")
+    ap.add_argument("--in-flight", type=int, default=0, help="--workload batch-128MB: files in flight per GPU (0 = by host cores)")
     ap.add_argument("--no-cli", action="store_true", help="skip the `bce -c` wall-time leg (host coders)")
     ap.add_argument("--ref-budget-s", type=float, default=420.0,
                     help="--impl reference: seconds one run may take; the whole workload is timed once when it fits")
@@ -455,6 +545,8 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
+        if args.workload == "batch-128MB" and args.files > 0:
+            return run_batch_workload(args, rank, world, local_rank)
         return run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:

@@ -110,6 +110,12 @@ enum { BCE_GPU_OPT_EMIT_BATCH_BYTES = 1, BCE_GPU_OPT_LOCAL_SORT_MIN = 2, BCE_GPU
        BCE_GPU_OPT_SLOT_ENTER_NODES = 4 };
 int bce_gpu_set_option(bce_gpu_ctx *ctx, int option, uint64_t value);
 
+/* Page-locked host memory for the caller's input and output buffers (File::File reads the whole file into one
+ * buffer, bce.cpp:842-856: read it into this and the upload is one DMA transfer instead of staged copies).
+ * Any host pointer is accepted everywhere; this is an optimisation, not a requirement. */
+void *bce_gpu_host_alloc(bce_gpu_ctx *ctx, size_t bytes);
+void bce_gpu_host_free(bce_gpu_ctx *ctx, void *p);
+
 /* ---- stage A: suffix sort / BWT ------------------------------------------------
  * Replaces File::rotate (bce.cpp:858-894) and File::bwt with its divbwt call into
  * libdivsufsort (bce.cpp:896-910, call :901, splice :902).

@@ -103,6 +103,19 @@ def test_single_process_queue_without_a_process_group(tmp_path):
     res = batch.compress_files([str(tmp_path / f"f{i}") for i in range(3)], str(tmp_path / "o"),
                                lambda d, cfg: (bytes(d[:2]), 1.0))
     assert [f.ok for f in res.files] == [True] * 3 and res.total.inputs == 3 and res.total.failed == 0
+    # two files in flight on one rank: two compressors, two worker threads, every file still exactly once
+    import threading
+    seen = []
+    def make(tag):
+        def fn(d, cfg):
+            seen.append((tag, threading.get_ident()))
+            return bytes([tag]) + bytes(d[:1]), 1.0
+        return fn
+    for i in range(3, 11):
+        (tmp_path / f"f{i}").write_bytes(b"y" * (10 + i))
+    res = batch.compress_files([str(tmp_path / f"f{i}") for i in range(11)], str(tmp_path / "o2"), [make(1), make(2)])
+    assert [f.index for f in res.files] == list(range(11)) and all(f.ok for f in res.files)
+    assert res.total.inputs == 11 and len(seen) == 11 and len({t for _, t in seen}) == 2
 
 
 def test_round_robin_shard_is_a_partition():

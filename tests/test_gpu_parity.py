@@ -282,3 +282,58 @@ def test_tile_local_sort_forced_on_small_inputs(frontend):
     finally:
         frontend.set_option(OPT_LOCAL_SORT_MIN, 0)
     assert local > 0, "the option did not force the tile-local sort"
+
+
+def test_error_paths_of_the_c_abi(frontend):
+    """Call-sequence and resource errors come back as codes with a message, never as a crash or a wrong result:
+    BCE_GPU_E_STATE for calls out of order, BCE_GPU_E_ARG for bad arguments, BCE_GPU_E_NOMEM / BCE_GPU_E_FRONTIER
+    when the scratch limit leaves no room for the level loop's frontier."""
+    import ctypes as C
+
+    from bce_b200 import Frontend, synth
+    from bce_b200.gpu import CseBatch, CseWords, EMIT_CODER, EMIT_SCAN, ScanBuckets
+    fe = Frontend(0)                                   # a second context on the same device: contexts share nothing
+    try:
+        lib, h = fe.lib, fe.h
+        assert lib.bce_gpu_cse_next(h, C.byref(CseBatch())) == -4            # no cse_begin yet
+        assert lib.bce_gpu_cse_next_words(h, C.byref(CseWords())) == -4
+        assert lib.bce_gpu_cse_next_buckets(h, C.byref(ScanBuckets())) == -4
+        assert lib.bce_gpu_cse_begin(h, None, 1000, (C.c_uint32 * 8)()) == -4  # no BWT resident
+        off, tup = C.c_uint32(), C.c_uint64()
+        assert lib.bce_gpu_front_resident(h, C.byref(off), C.byref(tup)) == -4  # no staged input
+        assert lib.bce_gpu_resident_checksum(h, (C.c_uint64 * 8)(), (C.c_uint64 * 8)()) == -4
+        assert lib.bce_gpu_bwt(h, None, 10, None, None, None) == -1
+        buf = (C.c_uint8 * 16)()
+        assert lib.bce_gpu_bwt(h, buf, 0, None, None, None) == -1              # n = 0 (the reference crashes, SURVEY.md Q2)
+        assert lib.bce_gpu_bwt(h, buf, 0x80000000, None, None, None) == -1     # n >= 2^31
+        assert lib.bce_gpu_set_option(h, 99, 1) == -1
+        assert lib.bce_gpu_set_emit_mode(h, 7, None) == -1
+        bad_cfg = (C.c_uint8 * 288)(*([9] * 288))
+        assert lib.bce_gpu_set_emit_mode(h, EMIT_CODER, bad_cfg) == -1
+        assert b"context bits" in lib.bce_gpu_last_error(h)
+
+        data = synth.generate("enwik-shaped", 2_000_000, 3)
+        # raw counts asked for while the run emits packed words
+        fe.set_emit_mode(EMIT_CODER)
+        offv, Cv = C.c_uint32(), (C.c_uint32 * 8)()
+        assert lib.bce_gpu_compress_front(h, data.ctypes.data, data.size, C.byref(offv), Cv) == 0
+        assert lib.bce_gpu_cse_next(h, C.byref(CseBatch())) == -4
+        assert lib.bce_gpu_cse_next_buckets(h, C.byref(ScanBuckets())) == -4   # needs BCE_EMIT_SCAN
+        fe.set_emit_mode(0)
+
+        # a scratch limit that leaves the level loop's frontier no room (the suffix sort takes what it needs)
+        L, off2, _ = fe.bwt(data)
+        want_L, want_off, _ = oracle.bwt(data)
+        assert off2 == want_off and bytes(L) == bytes(want_L)                   # the context works again after the errors
+        fe.set_scratch_limit(3 << 20)
+        rc = lib.bce_gpu_cse_begin(h, None, data.size, Cv)
+        if rc == 0:                                                             # the frontier budget is found out while running
+            b = CseBatch()
+            while rc == 0 and not b.done:
+                rc = lib.bce_gpu_cse_next(h, C.byref(b))
+        assert rc in (-2, -5), rc
+        assert len(lib.bce_gpu_last_error(h)) > 0
+        fe.set_scratch_limit(0)
+        assert host.compress(fe, data, threads=2) == host.compress(frontend, data, threads=2)
+    finally:
+        fe.close()

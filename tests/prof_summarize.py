@@ -21,8 +21,8 @@ def short(n):
 
 
 def launch_list():
-    shutil.copy(OUT / "launches_r1g_1gb.csv", PROF / "r1_launches_enwik1GB_final.csv")
-    lines = [l for l in open(PROF / "r1_launches_enwik1GB_final.csv") if not l.startswith("==")]
+    shutil.copy(OUT / "launches_r2_1gb.csv", PROF / "r2_launches_enwik1GB.csv")
+    lines = [l for l in open(PROF / "r2_launches_enwik1GB.csv") if not l.startswith("==")]
     r = list(csv.reader(lines))
     hdr = r[0]
     ci = {h: i for i, h in enumerate(hdr)}
@@ -41,9 +41,9 @@ def launch_list():
         return agg
 
     bench = json.loads(open(OUT / "bench_plain_for_ncu.json").read().strip().splitlines()[-1])
-    out = ["# Round 1 (final kernels): ncu launch list of the bench command, enwik-shaped 1 GB\n",
-           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline`",
-           f"(raw list: `r1_launches_enwik1GB_final.csv`, {len(data)} launches = 4 resident passes + 3 passes through the host-buffer API).",
+    out = ["# Round 2: ncu launch list of the bench command, enwik-shaped 1 GB\n",
+           "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-cli`",
+           f"(raw list: `r2_launches_enwik1GB.csv`, {len(data)} launches = 4 resident passes + 3 passes through the host-buffer API).",
            "Times under ncu are serialised and cold-cache; what must agree with the bench is each kernel's SHARE of the step.\n",
            f"Same command without ncu (same box, just before): value {bench['value']:.0f} MB/s, {bench['ms_per_step']:.1f} ms/step, "
            f"e2e {bench['e2e']['value']:.0f} MB/s; stage_ms {json.dumps({k: round(v, 1) for k, v in bench['stage_ms'].items()})}\n"]
@@ -60,20 +60,19 @@ def launch_list():
     out += ["## Shares in the un-profiled bench step (CUDA events)\n", "| stage | ms | share |", "|---|---:|---:|"]
     for k in ("ms_radix", "ms_cse", "ms_rerank", "ms_rekey", "ms_bwt_gather", "ms_wavelet", "ms_pack"):
         out.append(f"| {k[3:]} | {st[k]:.1f} | {100 * st[k] / tot:.1f} % |")
-    out.append("\n(`radix` = the `radix_onesweep_kernel` launches of the sorts; `rerank` = `rerank_kernel` + the one-pass "
-               "`radix_onesweep_kernel` partition + `scatter_ranks_kernel`; `cse` = all `cse_*` kernels.)")
-    (PROF / "r1_launches_enwik1GB_final.md").write_text("\n".join(out) + "\n")
+    out.append("\n(`radix` = the `radix_onesweep_kernel` launches of the sorts; `rerank` = `rerank_kernel` + `scatter_ranks_kernel`; `cse` = all `cse_*` kernels.)")
+    (PROF / "r2_launches_enwik1GB.md").write_text("\n".join(out) + "\n")
 
 
 def kernel_tables():
     stall_prefix = "smsp__average_warps_issue_stalled_"
-    out = ["# Round 1 (final kernels): `ncu --set full --clock-control none` captures, enwik-shaped 100 MB, packed (CODER) emission",
+    out = ["# Round 2: `ncu --set full --clock-control none` captures, enwik-shaped 100 MB, packed (CODER) emission",
            "", "Command: `ncu --set full --clock-control none --import-source on -k regex:<kernels> -c N python tests/gpu_trace.py enwik-shaped 100000000 2`",
-           "(first pass of a fresh process, `BCE_TRACE_WARM=0`; the reports `gpurun_out/prof_r1g_bwt.ncu-rep`, `prof_r1g_cse.ncu-rep` are scratch, not committed).",
+           "(first pass of a fresh process, `BCE_TRACE_WARM=0`; the reports `gpurun_out/prof_r2_bwt.ncu-rep`, `prof_r2_cse.ncu-rep` are scratch, not committed).",
            "One row per captured launch, values from `ncu -i <rep> --page raw --csv`. DRAM GB = dram__bytes_read.sum + dram__bytes_write.sum; "
            "ld/st s/r = L1 sectors per global load/store request (32 = every lane its own sector).", ""]
-    for f, title in (("prof_r1g_bwt", "Stage A kernels (first 22 launches: pack, round 0 sort, re-rank, partition, scatter, key rebuild, round 1 sort ...)"),
-                     ("prof_r1g_cse", "Stage A tail + stage B kernels (BWT gather, wavelet passes, level loop)")):
+    for f, title in (("prof_r2_bwt", "Stage A kernels (first 26 launches: round 0 sort, re-rank, scatter, tile sort of round 1 ...)"),
+                     ("prof_r2_cse", "Stage A tail + stage B kernels (binned BWT, wavelet passes, level loop)")):
         raw = subprocess.run(["ncu", "-i", str(OUT / f"{f}.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
         h, units = rows[0], rows[1]
@@ -109,7 +108,7 @@ def kernel_tables():
                        f"{g('sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {g('smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
                        f"{g('smsp__inst_executed.sum') / 1e6:.1f} | {st} |")
         out.append("")
-    (PROF / "r1_ncu_final_kernels.md").write_text("\n".join(out) + "\n")
+    (PROF / "r2_ncu_kernels.md").write_text("\n".join(out) + "\n")
 
 
 if __name__ == "__main__":

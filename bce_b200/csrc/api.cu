@@ -267,7 +267,7 @@ void bce_gpu_close(bce_gpu_ctx* h) {
   bce::cse_destroy(c);
   c->text.release(); c->bwt.release(); c->ranks.release(); c->scratch.release();
   c->small.release(); c->desc.release();
-  c->scan_tmp.release();
+  c->scan_tmp.release(); c->pack_tmp.release();
   c->pinned_small.release(); c->pinned_emit.release(); c->pinned_emit2.release(); c->pinned_io.release();
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->pass_ev) if (e) cudaEventDestroy(e);
@@ -395,9 +395,9 @@ int bce_gpu_cse_begin(bce_gpu_ctx* h, const uint8_t* L, uint32_t n, uint32_t C_o
   return BCE_GPU_OK;
 }
 
-static int next_words(Ctx* c, bce::CseWordBatch* wb) {
+static int next_words(Ctx* c, bce::CseWordBatch* wb, bool pack24 = false) {
   const auto t0 = std::chrono::steady_clock::now();
-  BCE_TRY(bce::cse_advance(c, false, wb));
+  BCE_TRY(bce::cse_advance(c, false, wb, pack24));
   c->stats.ms_cse_total += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return BCE_GPU_OK;
 }
@@ -427,6 +427,21 @@ int bce_gpu_cse_next_words(bce_gpu_ctx* h, bce_cse_words* out) {
   bce::CseWordBatch wb;
   BCE_TRY(next_words(c, &wb));
   for (int i = 0; i < 8; ++i) { out->words[i] = wb.words[i]; out->count[i] = wb.count[i]; }
+  out->done = wb.done;
+  return BCE_GPU_OK;
+}
+
+int bce_gpu_cse_next_words24(bce_gpu_ctx* h, bce_cse_words24* out) {
+  if (!h || !out) return BCE_GPU_E_ARG;
+  Ctx* c = static_cast<Ctx*>(h);
+  bce::begin_call(c);
+  if (!c->cse_active || c->cse_emit_mode_active != BCE_EMIT_CODER) {
+    bce::set_error(c, "cse_next_words24: needs a run started in BCE_EMIT_CODER mode");
+    return BCE_GPU_E_STATE;
+  }
+  bce::CseWordBatch wb;
+  BCE_TRY(next_words(c, &wb, true));
+  for (int i = 0; i < 8; ++i) { out->bytes[i] = reinterpret_cast<const uint8_t*>(wb.words[i]); out->count[i] = wb.count[i]; }
   out->done = wb.done;
   return BCE_GPU_OK;
 }

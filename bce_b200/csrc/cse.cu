@@ -19,10 +19,11 @@
 // The host alternates between the two on the kernels' request and drains the emission buffers.
 //
 // Emission is word based.  Raw mode writes the five arguments of set() (20 B, bce_tuple);
-// the packed modes write what the host coder actually consumes (4 B, 8 B when k > 31):
-//   coder  [esc:1|nb:5 @20|ctx:10 @10|k:5 @5|sym:5]   ctx = get_context index, bce.cpp:671-677,
-//          for the stream's configured context bits; esc: k > 31 was halved nb times
-//          (bce.cpp:507-510), a second word carries the nb low bits of the symbol
+// the packed modes write what the host coder actually consumes (one word; three when k > 31):
+//   coder  [esc:1 @23|ctx:10 @10|k:5 @5|sym:5]   ctx = get_context index, bce.cpp:671-677, for the
+//          stream's configured context bits; esc: k > 31 was halved nb times (bce.cpp:507-510), two
+//          more words carry nb and the nb low bits of the symbol: [low[0..19) @5|nb:5], [low >> 19].
+//          Every word is below 2^24, so a batch crosses PCIe as 3 bytes per word (cse_pack24_kernel)
 //   scan   [esc:1|nb:5 @26|q2:8 @18|q1:8 @10|k:5 @5|sym:5]   ScanCoder::set, bce.cpp:737-744
 //
 // Algorithmic HBM bytes: 48 B per node visit + 20 B per emitted count.
@@ -101,7 +102,7 @@ __device__ __forceinline__ unsigned long long vol_load64(const unsigned long lon
   return v;
 }
 
-// One emitted count -> words.  Returns the number of words (5 raw, 1 or 2 packed); e0..e2 hold
+// One emitted count -> words.  Returns the number of words (5 raw, 1 or 3 packed); e0..e2 hold
 // them (raw: sym, k, c1 -- the caller appends c2 = x1 and cs = x).
 __device__ __forceinline__ uint32_t count_words(const CseArgs& a, int level, uint32_t sym, uint32_t k,
                                                 uint32_t c1, uint32_t c2, uint32_t cs,
@@ -113,11 +114,12 @@ __device__ __forceinline__ uint32_t count_words(const CseArgs& a, int level, uin
     const uint32_t b = a.cfgbits[level][k];
     const uint32_t ctx = (((c1 << b) / cs) << b) | ((c2 << b) / cs);            // bce.cpp:674 (uint32 wrap)
     const uint32_t w = (ctx << 10) | (k << 5) | s;
-    e2 = 0;
-    if (nb == 0) { e0 = w; e1 = 0; return 1u; }
-    e0 = 0x80000000u | (nb << 20) | w;
-    e1 = sym & ((1u << nb) - 1u);
-    return 2u;
+    if (nb == 0) { e0 = w; e1 = e2 = 0; return 1u; }
+    const uint32_t low = sym & ((1u << nb) - 1u);                                  // nb <= 27
+    e0 = 0x800000u | w;
+    e1 = nb | ((low & 0x7FFFFu) << 5);
+    e2 = low >> 19;
+    return 3u;
   }
   while (k > 31u) { k = (k >> 1) + (~s & 1u); s >>= 1; ++nb; }                   // bce.cpp:738-741
   const uint32_t q1 = (c1 << 8) / cs, q2 = (c2 << 8) / cs;                        // bce.cpp:743
@@ -129,9 +131,11 @@ __device__ __forceinline__ void put_words(uint32_t* dst, uint32_t nw, uint32_t e
                                           uint32_t x1, uint32_t x) {
   dst[0] = e0;
   if (nw == 5u) { dst[1] = e1; dst[2] = e2; dst[3] = x1; dst[4] = x; }
-  else if (nw == 2u) dst[1] = e1;
+  else if (nw == 3u) { dst[1] = e1; dst[2] = e2; }
 }
-__device__ __forceinline__ uint32_t max_words(const CseArgs& a) { return a.emit_mode == kEmitRaw ? 5u : 2u; }
+__device__ __forceinline__ uint32_t max_words(const CseArgs& a) {
+  return a.emit_mode == kEmitRaw ? 5u : a.emit_mode == kEmitCoder ? 3u : 1u;
+}
 
 // Grid-wide barrier.  Every CTA adds one arrival; barrier number b (0-based, counted since
 // cse_begin) is passed when the counter reaches (b + 1) * gridDim.x.  The counter only grows,
@@ -204,6 +208,27 @@ __global__ void __launch_bounds__(256) cse_checksum_kernel(const uint32_t* __res
     ws += __shfl_xor_sync(0xffffffffu, ws, d);
   }
   if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], s); atomicAdd(&acc[1], ws); }
+}
+
+// Words below 2^24 leave as 3 bytes each: a thread turns 4 words into 12 bytes (three aligned 32-bit stores).
+__global__ void __launch_bounds__(256) cse_pack24_kernel(const uint32_t* __restrict__ words, unsigned long long count,
+                                                         uint32_t* __restrict__ out) {
+  const unsigned long long quads = (count + 3) / 4;
+  for (unsigned long long q = blockIdx.x * 256ull + threadIdx.x; q < quads; q += gridDim.x * 256ull) {
+    const unsigned long long j = 4 * q;
+    uint32_t w0, w1 = 0, w2 = 0, w3 = 0;
+    if (j + 4 <= count) {
+      const uint4 v = *reinterpret_cast<const uint4*>(words + j);          // emission buffers are 256-byte aligned
+      w0 = v.x; w1 = v.y; w2 = v.z; w3 = v.w;
+    } else {
+      w0 = words[j];
+      if (j + 1 < count) w1 = words[j + 1];
+      if (j + 2 < count) w2 = words[j + 2];
+    }
+    out[3 * q] = w0 | (w1 << 24);
+    out[3 * q + 1] = (w1 >> 8) | (w2 << 16);
+    out[3 * q + 2] = (w2 >> 16) | (w3 << 8);
+  }
 }
 
 // ---- bce -s: bucketing of a batch of BCE_EMIT_SCAN words (ScanCoder::set, bce.cpp:737-744) ---------------
@@ -668,7 +693,7 @@ int cse_begin(Ctx* c, uint32_t n) {
   CseArgs& a = H->args;
   a.emit_mode = c->emit_mode;
   memcpy(a.cfgbits, c->emit_cfg, sizeof a.cfgbits);
-  const size_t wmax = a.emit_mode == kEmitRaw ? 5 : 2;
+  const size_t wmax = a.emit_mode == kEmitRaw ? 5 : 3;      // words one count can take (scan: 1, sized like coder)
 
   // ---- sizing: frontier first (correctness), emission with what is left ------------
   const size_t budget = scratch_budget(c);
@@ -689,7 +714,7 @@ int cse_begin(Ctx* c, uint32_t n) {
   size_t arena_cap = 0, chunk_cap = 0, dir_cap = 0, slot_bytes = 0;
   int slot_grid = 0;
   if (want_slots) {
-    const void* fn = a.emit_mode == kEmitRaw ? (const void*)cse_slots_kernel<5> : (const void*)cse_slots_kernel<2>;
+    const void* fn = a.emit_mode == kEmitRaw ? (const void*)cse_slots_kernel<5> : (const void*)cse_slots_kernel<3>;
     int per_sm = 0;
     BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SL_THREADS, 0));
     slot_grid = per_sm * c->sm_count;
@@ -804,12 +829,12 @@ int cse_begin(Ctx* c, uint32_t n) {
   c->stats.gpu_launches++;
   BCE_CUDA(c, cudaGetLastError());
 
-  {   // wide kernel instances: raw counts need 5 staging words per node, packed ones 2
+  {   // wide kernel instances: raw counts need 5 staging words per node, packed ones 3
     const bool packed = a.emit_mode != kEmitRaw;
-    const void* f2 = packed ? (const void*)cse_wide_kernel<2, 2> : (const void*)cse_wide_kernel<2, 5>;
-    const void* f4 = packed ? (const void*)cse_wide_kernel<4, 2> : (const void*)cse_wide_kernel<4, 5>;
-    const size_t s2 = packed ? 2 * sizeof(WideStage<2, 2>) : 2 * sizeof(WideStage<2, 5>);
-    const size_t s4 = packed ? 2 * sizeof(WideStage<4, 2>) : 2 * sizeof(WideStage<4, 5>);
+    const void* f2 = packed ? (const void*)cse_wide_kernel<2, 3> : (const void*)cse_wide_kernel<2, 5>;
+    const void* f4 = packed ? (const void*)cse_wide_kernel<4, 3> : (const void*)cse_wide_kernel<4, 5>;
+    const size_t s2 = packed ? 2 * sizeof(WideStage<2, 3>) : 2 * sizeof(WideStage<2, 5>);
+    const size_t s4 = packed ? 2 * sizeof(WideStage<4, 3>) : 2 * sizeof(WideStage<4, 5>);
     {
       int p2 = 0, p4 = 0;
       BCE_CUDA(c, cudaFuncSetAttribute(f2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s2)));
@@ -1057,7 +1082,7 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
 // One batch of emitted words.  resident: counts stay in device memory (measurement), the
 // whole loop runs here.  Otherwise a batch is copied to pinned host memory on the copy stream
 // while the kernels already fill the other buffer set with the next batch.
-int cse_advance(Ctx* c, bool resident, CseWordBatch* out) {
+int cse_advance(Ctx* c, bool resident, CseWordBatch* out, bool pack24) {
   if (!c->cse_active || !c->cse) { set_error(c, "cse_next without cse_begin"); return BCE_GPU_E_STATE; }
   CseHost* H = c->cse;
   if (out) memset(out, 0, sizeof *out);
@@ -1079,24 +1104,37 @@ int cse_advance(Ctx* c, bool resident, CseWordBatch* out) {
     if (H->sets == 2) H->fill_set ^= 1;
   }
   // copy the pending batch out on the copy stream ...
-  size_t total = 0;
-  for (int l = 0; l < 8; ++l) total += H->pending_cnt[l];
+  if (pack24 && H->args.emit_mode != kEmitCoder) { set_error(c, "24-bit words need BCE_EMIT_CODER"); return BCE_GPU_E_STATE; }
+  const size_t unit = pack24 ? 3 : 4;                   // bytes per word on the host side
+  size_t bytes = 64, at_b[8];
+  for (int l = 0; l < 8; ++l) {                           // the pack kernel writes whole groups of 4 words = 12 bytes
+    at_b[l] = bytes;
+    bytes += ((pack24 ? (H->pending_cnt[l] + 3) / 4 * 12 : H->pending_cnt[l] * unit) + 15) & ~size_t(15);
+  }
   PinnedBuf& pin = H->pinned_flip ? c->pinned_emit2 : c->pinned_emit;
   H->pinned_flip ^= 1;
-  BCE_TRY(pin.ensure(c, (total + 16) * sizeof(uint32_t)));
-  uint32_t* hp = pin.as<uint32_t>();
+  BCE_TRY(pin.ensure(c, bytes));
+  char* hp = pin.as<char>();
+  if (pack24) BCE_TRY(c->pack_tmp.ensure(c, bytes));
   cudaStream_t cs = c->copy_stream;
   BCE_CUDA(c, cudaEventRecord(c->ev[6], c->stream));            // everything computed so far ...
   BCE_CUDA(c, cudaStreamWaitEvent(cs, c->ev[6], 0));            // ... is visible to the copies
   BCE_CUDA(c, cudaEventRecord(c->ev[4], cs));
-  size_t at = 0;
   for (int l = 0; l < 8; ++l) {
-    out->words[l] = hp + at;
+    out->words[l] = reinterpret_cast<const uint32_t*>(hp + at_b[l]);
     out->count[l] = H->pending_cnt[l];
-    if (H->pending_cnt[l])
-      BCE_CUDA(c, cudaMemcpyAsync(hp + at, H->emit_dev[H->pending_set][l], H->pending_cnt[l] * sizeof(uint32_t),
-                                  cudaMemcpyDeviceToHost, cs));
-    at += H->pending_cnt[l];
+    if (!H->pending_cnt[l]) continue;
+    const uint32_t* src = H->emit_dev[H->pending_set][l];
+    if (pack24) {                                               // packed on the copy stream: runs beside the next batch's kernels
+      uint32_t* pk = reinterpret_cast<uint32_t*>(c->pack_tmp.as<char>() + at_b[l]);
+      const size_t quads = (H->pending_cnt[l] + 3) / 4;
+      const int grid = int(std::min<size_t>((quads + 255) / 256, size_t(c->sm_count) * 4));
+      cse_pack24_kernel<<<grid, 256, 0, cs>>>(src, H->pending_cnt[l], pk);
+      c->stats.gpu_launches++;
+      BCE_CUDA(c, cudaMemcpyAsync(hp + at_b[l], pk, H->pending_cnt[l] * 3, cudaMemcpyDeviceToHost, cs));
+    } else {
+      BCE_CUDA(c, cudaMemcpyAsync(hp + at_b[l], src, H->pending_cnt[l] * sizeof(uint32_t), cudaMemcpyDeviceToHost, cs));
+    }
   }
   BCE_CUDA(c, cudaEventRecord(c->ev[5], cs));
   const bool this_done = H->pending_done;

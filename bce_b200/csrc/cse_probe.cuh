@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256, MINB) cse_slot_probe_kernel(CseArgs a) {
     uint32_t* __restrict__ ga = a.fa[nxt][ln];
     uint32_t* __restrict__ gb = a.fb[nxt][ln];
     const uint32_t zbase = slot, obase = a.cap / 2 + slot;
-    uint32_t* __restrict__ ew = a.emit[l] + size_t(slot) * 2u;
+    uint32_t* __restrict__ ew = a.emit[l] + size_t(slot) * 3u;
     const uint32_t one_base = a.C[ln];
     uint32_t cz = 0, co = 0, ce = 0;
 #pragma unroll
@@ -102,13 +102,9 @@ __global__ void __launch_bounds__(256, MINB) cse_slot_probe_kernel(CseArgs a) {
       cz += __popc(bz);
       co += __popc(bo);
       if (be) {
-        const unsigned b2 = __ballot_sync(0xffffffffu, nw == 2u);
-        if (nw && nw <= 2u) {
-          uint32_t* d = ew + ce + __popc(be & lt_mask) + __popc(b2 & lt_mask);
-          d[0] = e0;
-          if (nw == 2u) d[1] = e1;
-        }
-        ce += __popc(be) + __popc(b2);
+        const unsigned b3 = __ballot_sync(0xffffffffu, nw == 3u);
+        if (nw && nw <= 3u) put_words(ew + ce + __popc(be & lt_mask) + 2u * __popc(b3 & lt_mask), nw, e0, e1, e2, x1, x);
+        ce += __popc(be) + 2u * __popc(b3);
       }
     }
     if (lane == 0 && t < 3u * a.desc_tiles) counts[t] = cz | (co << 8) | (ce << 16);

@@ -349,9 +349,9 @@ __global__ void __launch_bounds__(SL_THREADS, SL_MINB) cse_slots_kernel(CseArgs 
               if (nw) put_words(ew + ce + 5u * __popc(be & lt_mask), nw, e0, e1, e2, x1, x);
               ce += 5u * __popc(be);
             } else {
-              const unsigned b2 = __ballot_sync(0xffffffffu, nw == 2u);
-              if (nw) put_words(ew + ce + __popc(be & lt_mask) + __popc(b2 & lt_mask), nw, e0, e1, e2, x1, x);
-              ce += __popc(be) + __popc(b2);
+              const unsigned b3 = __ballot_sync(0xffffffffu, nw == 3u);      // k > 31: two more words
+              if (nw) put_words(ew + ce + __popc(be & lt_mask) + 2u * __popc(b3 & lt_mask), nw, e0, e1, e2, x1, x);
+              ce += __popc(be) + 2u * __popc(b3);
             }
           }
         }

@@ -42,18 +42,21 @@ void ArchiveWriter::feed_words(const bce_cse_words& batch, int threads) {
 
 void ArchiveWriter::worker(int i) {
   for (;;) {
-    const uint32_t* words;
+    const void* words;
     size_t count;
+    bool b24;
     {
       std::unique_lock<std::mutex> lk(mu_);
       cv_work_.wait(lk, [&] { return stop_ || job_ready_[i]; });
       if (stop_ && !job_ready_[i]) return;
       words = job_words_[i];
       count = job_count_[i];
+      b24 = job_24_[i];
       job_ready_[i] = false;
     }
     const auto t0 = std::chrono::steady_clock::now();
-    streams_[i]->packed(words, count);
+    if (b24) streams_[i]->packed24(static_cast<const uint8_t*>(words), count);
+    else streams_[i]->packed(static_cast<const uint32_t*>(words), count);
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -71,6 +74,22 @@ void ArchiveWriter::begin_words(const bce_cse_words& batch) {
     if (!batch.count[i]) continue;
     job_words_[i] = batch.words[i];
     job_count_[i] = batch.count[i];
+    job_24_[i] = false;
+    job_ready_[i] = true;
+    ++jobs_open_;
+  }
+  cv_work_.notify_all();
+}
+
+void ArchiveWriter::begin_words24(const bce_cse_words24& batch) {
+  if (pool_.empty())
+    for (int i = 0; i < 8; ++i) pool_.emplace_back(&ArchiveWriter::worker, this, i);
+  std::lock_guard<std::mutex> lk(mu_);
+  for (int i = 0; i < 8; ++i) {
+    if (!batch.count[i]) continue;
+    job_words_[i] = batch.bytes[i];
+    job_count_[i] = batch.count[i];
+    job_24_[i] = true;
     job_ready_[i] = true;
     ++jobs_open_;
   }

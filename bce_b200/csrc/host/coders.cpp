@@ -186,25 +186,39 @@ void StreamEncoder::count(uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2, ui
   ContextModel::bump(row, k, sym);
 }
 
-void StreamEncoder::packed(const uint32_t* words, size_t count) {
+// One packed count (include/bce_gpu.h, BCE_EMIT_CODER): W(j) reads word j of the batch.
+template <class W>
+static inline void code_packed(RangeEncoder& rc, ContextModel& model, size_t count, W word) {
   for (size_t i = 0; i < count; ++i) {
-    const uint32_t w = words[i];
-    if (w >> 31) {                                                  // k > 31: nb uniform bits first (bce.cpp:507-510)
-      const uint32_t nb = (w >> 20) & 31u, low = words[++i];
-      for (uint32_t j = 0; j < nb; ++j) rc_.put_uniform((low >> j) & 1u, 2);
+    const uint32_t w = word(i);
+    if (w & 0x800000u) {                                            // k > 31: nb uniform bits first (bce.cpp:507-510)
+      const uint32_t w1 = word(i + 1), w2 = word(i + 2);
+      i += 2;
+      const uint32_t nb = w1 & 31u, low = (w1 >> 5) | (w2 << 19);
+      for (uint32_t j = 0; j < nb; ++j) rc.put_uniform((low >> j) & 1u, 2);
     }
     const uint32_t sym = w & 31u, k = (w >> 5) & 31u, ctx = (w >> 10) & 1023u;
-    uint8_t* row = model_.row_at(k, ctx);
+    uint8_t* row = model.row_at(k, ctx);
     uint32_t below = sym, total = k;                                // bce.cpp:514-518
     for (uint32_t j = 0; j < sym; ++j) below += row[j];
     total += ContextModel::sum(row, k);
-    rc_.put(below, uint32_t(row[sym]) + 1, total);
+    rc.put(below, uint32_t(row[sym]) + 1, total);
     ContextModel::bump(row, k, sym);
   }
 }
 
+void StreamEncoder::packed(const uint32_t* words, size_t count) {
+  code_packed(rc_, model_, count, [words](size_t j) { return words[j]; });
+}
+
+void StreamEncoder::packed24(const uint8_t* b, size_t count) {
+  code_packed(rc_, model_, count, [b](size_t j) {
+    return uint32_t(b[3 * j]) | (uint32_t(b[3 * j + 1]) << 8) | (uint32_t(b[3 * j + 2]) << 16);
+  });
+}
+
 size_t pack_count(int mode, const uint8_t* bits_row, uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2,
-                  uint32_t cs, uint32_t out[2]) {
+                  uint32_t cs, uint32_t out[3]) {
   uint32_t nb = 0, s = sym;
   if (mode == 1) {                                                  // BCE_EMIT_CODER
     while (k > uint32_t(kMaxAdaptive)) { k = (k + (~s & 1u)) >> 1; s >>= 1; ++nb; }
@@ -212,9 +226,11 @@ size_t pack_count(int mode, const uint8_t* bits_row, uint32_t sym, uint32_t k, u
     const uint32_t ctx = (((c1 << b) / cs) << b) | ((c2 << b) / cs);
     const uint32_t w = (ctx << 10) | (k << 5) | s;
     if (!nb) { out[0] = w; return 1; }
-    out[0] = 0x80000000u | (nb << 20) | w;
-    out[1] = sym & ((1u << nb) - 1u);
-    return 2;
+    const uint32_t low = sym & ((1u << nb) - 1u);
+    out[0] = 0x800000u | w;
+    out[1] = nb | ((low & 0x7FFFFu) << 5);
+    out[2] = low >> 19;
+    return 3;
   }
   while (k > uint32_t(kMaxAdaptive)) { k = (k >> 1) + (~s & 1u); s >>= 1; ++nb; }     // BCE_EMIT_SCAN
   const uint32_t q1 = (c1 << 8) / cs, q2 = (c2 << 8) / cs;

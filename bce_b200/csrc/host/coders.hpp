@@ -106,6 +106,7 @@ class StreamEncoder {
   void varint(uint32_t v);                                        // VCoder::setv
   // BCE_EMIT_CODER words (include/bce_gpu.h): context index and k > 31 halving done on the device
   void packed(const uint32_t* words, size_t count);
+  void packed24(const uint8_t* bytes, size_t count);              // the same words, 3 little-endian bytes each
   void finish() { rc_.finish(); }
   const std::vector<uint16_t>& words() const { return rc_.words(); }
 
@@ -130,7 +131,7 @@ class StreamDecoder {
 // context bits (0..5) that minimises the simulated adaptive code length.
 // host-side packer with the device's word formats (tests, and callers that hold raw counts)
 size_t pack_count(int mode, const uint8_t* bits_row, uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2,
-                  uint32_t cs, uint32_t out[2]);
+                  uint32_t cs, uint32_t out[3]);
 
 class ScanCollector {
  public:

@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "bce_gpu_stage_input", "bce_gpu_front_resident", "bce_gpu_unbwt",
     "bce_gpu_set_emit_mode", "bce_gpu_cse_next_words", "bce_gpu_set_option",
     "bce_gpu_resident_checksum", "bce_gpu_cse_next_buckets", "bce_gpu_host_alloc", "bce_gpu_host_free",
+    "bce_gpu_cse_next_words24",
 ]
 OPT_EMIT_BATCH_BYTES, OPT_LOCAL_SORT_MIN, OPT_RESIDENT_CHECKSUM, OPT_SLOT_ENTER_NODES = 1, 2, 3, 4
 
@@ -48,6 +49,10 @@ class CseBatch(C.Structure):
 
 class CseWords(C.Structure):
     _fields_ = [("words", C.POINTER(C.c_uint32) * 8), ("count", C.c_size_t * 8), ("done", C.c_int)]
+
+
+class CseWords24(C.Structure):
+    _fields_ = [("bytes", C.POINTER(C.c_uint8) * 8), ("count", C.c_size_t * 8), ("done", C.c_int)]
 
 
 class ScanBucket(C.Structure):
@@ -114,6 +119,7 @@ def load_library() -> C.CDLL:
     lib.bce_gpu_set_scratch_limit.argtypes = [vp, C.c_size_t]
     lib.bce_gpu_set_option.argtypes = [vp, C.c_int, C.c_uint64]
     lib.bce_gpu_cse_next_buckets.argtypes = [vp, C.POINTER(ScanBuckets)]
+    lib.bce_gpu_cse_next_words24.argtypes = [vp, C.POINTER(CseWords24)]
     lib.bce_gpu_host_alloc.argtypes = [vp, C.c_size_t]
     lib.bce_gpu_host_alloc.restype = vp
     lib.bce_gpu_host_free.argtypes = [vp, vp]
@@ -321,7 +327,7 @@ class Frontend:
             self.set_emit_mode(EMIT_RAW)
         return int(off.value), [int(x) for x in Cv], batches
 
-    def compress_front_discard(self, data):
+    def compress_front_discard(self, data, words24: bool = False):
         """Same call sequence a consumer makes (fused front end, then batches until done) in the
         context's current emission mode; the batches are left in pinned memory (bench e2e leg).
         Returns (offset, total 32-bit words handed back)."""
@@ -329,14 +335,40 @@ class Frontend:
         off = C.c_uint32()
         Cv = (C.c_uint32 * 8)()
         self._check(self.lib.bce_gpu_compress_front(self.h, T.ctypes.data, T.size, C.byref(off), Cv))
-        batch = CseWords()
+        batch = CseWords24() if words24 else CseWords()
+        nxt = self.lib.bce_gpu_cse_next_words24 if words24 else self.lib.bce_gpu_cse_next_words
         total = 0
         while True:
-            self._check(self.lib.bce_gpu_cse_next_words(self.h, C.byref(batch)))
+            self._check(nxt(self.h, C.byref(batch)))
             total += sum(int(batch.count[i]) for i in range(8))
             if batch.done:
                 break
         return int(off.value), total
+
+    def compress_front_words24(self, data, cfg: bytes | None = None):
+        """Fused front end, BCE_EMIT_CODER words as the 3-byte form of bce_gpu_cse_next_words24, unpacked to uint32
+        arrays again: (offset, C[8], 8 word arrays)."""
+        T = _as_u8(data)
+        self.set_emit_mode(EMIT_CODER, cfg)
+        try:
+            off = C.c_uint32()
+            Cv = (C.c_uint32 * 8)()
+            self._check(self.lib.bce_gpu_compress_front(self.h, T.ctypes.data, T.size, C.byref(off), Cv))
+            streams = [[] for _ in range(8)]
+            batch = CseWords24()
+            while True:
+                self._check(self.lib.bce_gpu_cse_next_words24(self.h, C.byref(batch)))
+                for i in range(8):
+                    cnt = int(batch.count[i])
+                    if cnt:
+                        b = np.ctypeslib.as_array((C.c_uint8 * (3 * cnt)).from_address(C.addressof(batch.bytes[i].contents)))
+                        b = b.reshape(cnt, 3).astype(np.uint32)
+                        streams[i].append(b[:, 0] | (b[:, 1] << np.uint32(8)) | (b[:, 2] << np.uint32(16)))
+                if batch.done:
+                    break
+        finally:
+            self.set_emit_mode(EMIT_RAW)
+        return int(off.value), [int(x) for x in Cv], [np.concatenate(s) if s else np.zeros(0, dtype=np.uint32) for s in streams]
 
     # -- device-resident measurement -------------------------------------------------------
     def stage_input(self, data):

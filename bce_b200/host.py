@@ -16,7 +16,7 @@ HOST_SYMBOLS = [
     "bce_scan_begin", "bce_scan_feed", "bce_scan_finish", "bce_compress_buffer", "bce_scan_buffer",
     "bce_host_default_config", "bce_host_free",
     "bce_archive_feed_words", "bce_scan_feed_words", "bce_host_pack_counts", "bce_decode_buffer",
-    "bce_archive_begin_words", "bce_archive_wait", "bce_scan_feed_buckets",
+    "bce_archive_begin_words", "bce_archive_wait", "bce_scan_feed_buckets", "bce_archive_begin_words24",
 ]
 
 
@@ -93,7 +93,7 @@ def pack_counts(mode: int, streams, cfg: bytes | None = None):
     out = []
     for i, s in enumerate(streams):
         a = np.ascontiguousarray(s, dtype=np.uint32)
-        w = np.zeros(2 * a.shape[0] + 2, dtype=np.uint32)
+        w = np.zeros(3 * a.shape[0] + 3, dtype=np.uint32)
         nw = lib.bce_host_pack_counts(mode, cfgbuf.ctypes.data if cfgbuf is not None else None, i,
                                       a.ctypes.data, a.shape[0], w.ctypes.data)
         out.append(w[:nw].copy())

@@ -367,12 +367,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     # ---- e2e leg: host buffers through the C ABI -----------------------------------------------
     for _ in range(max(2, args.warmup // 2)):             # both pinned batch buffers get allocated here
-        fe.compress_front_discard(host_in)
+        fe.compress_front_discard(host_in, words24=True)
     barrier()
     t0 = time.perf_counter()
     counts = 0
     for _ in range(args.steps):
-        _, counts = fe.compress_front_discard(host_in)
+        _, counts = fe.compress_front_discard(host_in, words24=True)
     my_e2e_ms = (time.perf_counter() - t0) * 1e3            # this rank alone, before it waits for the others
     barrier()
     e2e_ms = maxreduce((time.perf_counter() - t0) * 1e3)
@@ -381,7 +381,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # every rank's own e2e numbers (the job's e2e is the slowest rank's): where the time of a slow rank goes
     my_e2e = {"rank": rank, "e2e_ms_per_step": my_e2e_ms / args.steps, "ms_h2d": st_e2e["ms_h2d"], "ms_d2h": st_e2e["ms_d2h"],
               "ms_bwt_total": st_e2e["ms_bwt_total"], "ms_cse_total": st_e2e["ms_cse_total"],
-              "d2h_GBps": (int(counts) * 4 / 1e9) / (st_e2e["ms_d2h"] / 1e3) if st_e2e["ms_d2h"] > 0 else None,
+              "d2h_GBps": (int(counts) * 3 / 1e9) / (st_e2e["ms_d2h"] / 1e3) if st_e2e["ms_d2h"] > 0 else None,
               "h2d_GBps": (nbytes / 1e9) / (st_e2e["ms_h2d"] / 1e3) if st_e2e["ms_h2d"] > 0 else None}
     if world > 1:
         e2e_ranks = [None] * world
@@ -429,8 +429,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         note = "one launch runs all rounds of the level loop"
     achieved = k_bytes / (k_ms / 1e3) / 1e9
     traffic, traffic_src = None, None
-    try:                                   # measured DRAM bytes per algorithmic byte (ncu), see profiles/r1_traffic.json
-        tj = json.loads((Path(__file__).resolve().parent / "profiles" / "r1_traffic.json").read_text())
+    try:                                   # measured DRAM bytes per algorithmic byte (ncu), see profiles/r2_traffic.json
+        tj = json.loads((Path(__file__).resolve().parent / "profiles" / "r2_traffic.json").read_text())
         ent = tj["radix_onesweep_kernel" if radix_ms >= cse_ms else "cse_level_loop"]
         traffic, traffic_src = ent["ratio"] * k_bytes, f"{ent['ratio']} x algorithmic bytes of this launch; " + ent["source"]
     except Exception:
@@ -489,12 +489,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes,
-                    "d2h_bytes_per_step": int(counts) * 4 + 64, "emission": "BCE_EMIT_CODER packed words", "ms_per_step": e2e_ms / args.steps,
+                    "d2h_bytes_per_step": int(counts) * 3 + 64,
+                    "emission": "BCE_EMIT_CODER words, 3 bytes each (bce_gpu_cse_next_words24)", "ms_per_step": e2e_ms / args.steps,
                     "ms_h2d": st_e2e["ms_h2d"], "ms_d2h": st_e2e["ms_d2h"],
                     "ms_bwt_total": st_e2e["ms_bwt_total"], "ms_cse_total": st_e2e["ms_cse_total"],
                     "cse_launches": st_e2e["cse_launches"],
                     "per_rank": e2e_ranks,
-                    "aggregate_d2h_GBps": sum(int(counts) * 4 for _ in range(world)) / 1e9 / (e2e_ms / args.steps / 1e3),
+                    "aggregate_d2h_GBps_over_the_step": world * int(counts) * 3 / 1e9 / (e2e_ms / args.steps / 1e3),
                     "note": "ms_d2h is copy time on the copy stream; it runs under the level-loop kernels of the next "
                             "batch, so the step is max(kernels, copies) per batch, not their sum"},
             "e2e_cli": e2e_cli,

@@ -145,11 +145,13 @@ int bce_gpu_cse_next(bce_gpu_ctx *ctx, bce_cse_batch *out);
 
 /* ---- packed emission (what `bce -c` / `bce -s` of this repository use) ----------------
  * Instead of the five raw arguments (20 B) the device can emit what the host coder consumes:
- *   BCE_EMIT_CODER  one word  [0|nb=0|ctx:10 @10|k:5 @5|sym:5]  with ctx = the context index of
+ *   BCE_EMIT_CODER  one word  [ctx:10 @10|k:5 @5|sym:5]  with ctx = the context index of
  *                   AdaptiveCoder::get_context (bce.cpp:671-677) for the stream's configured
  *                   context bits cfg288[stream][k]; when the reference would halve k > 31
- *                   (bce.cpp:507-510) nb times: [1|nb:5 @20|ctx|k'|sym'] followed by one word
- *                   with the nb low bits of the symbol (coded uniformly, LSB first)
+ *                   (bce.cpp:507-510) nb times: [1 @23|ctx|k'|sym'] followed by two words
+ *                   [low[0..19) @5|nb:5] and [low >> 19] with the nb low bits of the symbol (coded
+ *                   uniformly, LSB first).  Every word is below 2^24: bce_gpu_cse_next_words24 hands
+ *                   the same words back as 3 bytes each (a quarter less over PCIe)
  *   BCE_EMIT_SCAN   one word  [esc|nb:5 @26|q2:8 @18|q1:8 @10|k:5 @5|sym:5], q = (c << 8) / cs,
  *                   halving rule of ScanCoder::set (bce.cpp:737-744)
  * set_emit_mode applies to the following cse_begin / compress_front calls of the context.
@@ -162,6 +164,14 @@ typedef struct bce_cse_words {
 } bce_cse_words;
 int bce_gpu_set_emit_mode(bce_gpu_ctx *ctx, int mode, const uint8_t *cfg288);
 int bce_gpu_cse_next_words(bce_gpu_ctx *ctx, bce_cse_words *out);
+/* BCE_EMIT_CODER only: the batch as 3 little-endian bytes per word (word j of stream i =
+ * bytes[i][3j] | bytes[i][3j+1] << 8 | bytes[i][3j+2] << 16), packed on the device before the copy. */
+typedef struct bce_cse_words24 {
+  const uint8_t *bytes[8];    /* pinned host memory, valid as bce_cse_batch: until the call after the next */
+  size_t count[8];            /* words (3 bytes each) */
+  int done;
+} bce_cse_words24;
+int bce_gpu_cse_next_words24(bce_gpu_ctx *ctx, bce_cse_words24 *out);
 
 /* ---- `bce -s`: counts bucketed on the device ------------------------------------------------
  * ScanCoder::set (bce.cpp:737-744) appends every symbol to stat_[k][(q2 << 16) | q1]; its flush

@@ -32,6 +32,7 @@ int bce_archive_feed_words(bce_archive_writer *w, const bce_cse_words *batch, in
  * reference forks its eight coders inside the level loop, bce.cpp:1250-1252, :1302); wait blocks until the
  * batch is coded.  The batch's memory must stay valid until then; one batch in flight at a time. */
 int bce_archive_begin_words(bce_archive_writer *w, const bce_cse_words *batch);
+int bce_archive_begin_words24(bce_archive_writer *w, const bce_cse_words24 *batch);   /* bce_gpu_cse_next_words24 batches */
 int bce_archive_wait(bce_archive_writer *w);
 /* flush, header (n, offset, sizes), concatenate; *words is malloc'd (bce_host_free). */
 int bce_archive_finish(bce_archive_writer *w, uint32_t offset, uint16_t **words, size_t *nwords);
@@ -52,7 +53,7 @@ int bce_compress_buffer(bce_gpu_ctx *ctx, const uint8_t *T, uint32_t n, const ui
 int bce_scan_buffer(bce_gpu_ctx *ctx, const uint8_t *T, uint32_t n, uint8_t cfg288_out[288]);
 
 /* host-side packer with the device's word formats (mode = BCE_EMIT_CODER / BCE_EMIT_SCAN);
- * words must hold 2 * count entries; returns the number of words written */
+ * words must hold 3 * count entries; returns the number of words written */
 size_t bce_host_pack_counts(int mode, const uint8_t *cfg288, int stream, const bce_tuple *t, size_t count,
                             uint32_t *words);
 

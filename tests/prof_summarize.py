@@ -73,7 +73,9 @@ def kernel_tables():
            "ld/st s/r = L1 sectors per global load/store request (32 = every lane its own sector).", ""]
     for f, title in (("prof_r2_bwt", "Stage A kernels (first 26 launches: round 0 sort, re-rank, scatter, tile sort of round 1 ...)"),
                      ("prof_r2_cse", "Stage A tail + stage B kernels (binned BWT, wavelet passes, level loop)")):
-        raw = subprocess.run(["ncu", "-i", str(OUT / f"{f}.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        csv_path = OUT / f"{f}_raw.csv"                      # written on the GPU box: the .ncu-rep files are too large to bring back
+        raw = csv_path.read_text() if csv_path.exists() else subprocess.run(
+            ["ncu", "-i", str(OUT / f"{f}.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
         h, units = rows[0], rows[1]
         ci = {k: i for i, k in enumerate(h)}

@@ -145,10 +145,15 @@ __device__ __forceinline__ bool grid_barrier(CseDeviceState* S, unsigned long lo
   bool ok = true;
   if (threadIdx.x == 0) {
     const unsigned long long target = (index + 1) * gridDim.x;
-    __threadfence();
-    atomicAdd(&S->arrivals, 1ull);
+    // release on the arrival, acquire on the poll: what the CTA wrote before is visible to every CTA that sees the
+    // count complete (cumulative through the block barrier above), without the two sequentially-consistent fences
+    // (MEMBAR.SC.GPU) the first version paid per round -- rounds of small frontiers are nothing but latency
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(&S->arrivals), "l"(1ull) : "memory");
     uint32_t spins = 0;
-    while (vol_load64(&S->arrivals) < target) {
+    for (;;) {
+      unsigned long long seen;
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(&S->arrivals) : "memory");
+      if (seen >= target) break;
       if (++spins > (1u << 22)) {
         atomicExch(&S->barrier_fail, round + 1);
         atomicExch(&S->err, 2u);
@@ -157,7 +162,6 @@ __device__ __forceinline__ bool grid_barrier(CseDeviceState* S, unsigned long lo
       }
       if (spins > 32) __nanosleep(20);
     }
-    __threadfence();
   }
   __syncthreads();
   return ok;

@@ -79,7 +79,7 @@ int next_tag(Ctx* c) {
 // (the runtime stages it); large pageable copies go through our own pinned staging buffer
 // in chunks so that the copy engine runs at pinned speed.
 constexpr size_t kStageChunk = size_t(64) << 20;
-static bool is_pinned(const void* p) {
+bool is_pinned(const void* p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return at.type == cudaMemoryTypeHost;
@@ -162,6 +162,23 @@ static void begin_call(Ctx* c) {
 }
 
 static int upload_text(Ctx* c, const uint8_t* T, uint32_t n) {
+  if (c->prefetch_pending) {                           // bce_gpu_prefetch_input: the copy may already be there
+    c->prefetch_pending = false;
+    const bool arrived = cudaEventQuery(c->ev_prefetch[1]) == cudaSuccess;
+    BCE_CUDA(c, cudaEventSynchronize(c->ev_prefetch[1]));
+    BCE_TRACE("prefetched input: %s, %s", arrived ? "already on the device" : "still in flight",
+              (c->prefetch_src == T && c->prefetch_n == n) ? "adopted" : "another input: discarded");
+    if (c->prefetch_src == T && c->prefetch_n == n) {
+      float ms = 0;
+      BCE_CUDA(c, cudaEventElapsedTime(&ms, c->ev_prefetch[0], c->ev_prefetch[1]));
+      c->stats.ms_h2d += ms;                           // the copy's own duration; it ran beside the previous level loop
+      c->n = n;
+      c->text_resident = true;
+      c->bwt_resident = false;
+      c->ranks_resident = false;
+      return BCE_GPU_OK;
+    }
+  }
   BCE_TRY(c->text.ensure(c, size_t(n) + 128));
   cudaEvent_t a = c->ev[4], b = c->ev[5];
   BCE_CUDA(c, cudaEventRecord(a, c->stream));
@@ -247,7 +264,9 @@ int bce_gpu_open(int device, bce_gpu_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->total_mem = prop.totalGlobalMem;
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+            cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&c->ev_prefetch[0]) == cudaSuccess && cudaEventCreate(&c->ev_prefetch[1]) == cudaSuccess;
   for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
   for (int i = 0; ok && i < 256; ++i) ok = cudaEventCreate(&c->pass_ev[i]) == cudaSuccess;
   if (ok) ok = bce::radix_init_device(c) == BCE_GPU_OK;      // per-device function attributes
@@ -273,6 +292,8 @@ void bce_gpu_close(bce_gpu_ctx* h) {
   for (auto& e : c->pass_ev) if (e) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamDestroy(c->h2d_stream); }
+  for (auto& e : c->ev_prefetch) if (e) cudaEventDestroy(e);
   delete c;
 }
 
@@ -499,6 +520,26 @@ int bce_gpu_compress_front(bce_gpu_ctx* h, const uint8_t* T, uint32_t n, uint32_
   BCE_TRY(bce::run_cse_begin(c, n));
   if (offset_out) *offset_out = c->offset;
   if (C_out) for (int i = 0; i < 8; ++i) C_out[i] = c->C[i];
+  return BCE_GPU_OK;
+}
+
+int bce_gpu_prefetch_input(bce_gpu_ctx* h, const uint8_t* T, uint32_t n) {
+  if (!h || !T) return BCE_GPU_E_ARG;
+  Ctx* c = static_cast<Ctx*>(h);
+  bce::begin_call(c);
+  BCE_TRY(bce::check_n(c, n));
+  if (!bce::is_pinned(T)) return BCE_GPU_OK;           // pageable memory cannot be copied asynchronously: the next call uploads it
+  if (c->prefetch_pending) { BCE_CUDA(c, cudaEventSynchronize(c->ev_prefetch[1])); c->prefetch_pending = false; }
+  // the text buffer is free once the BWT exists (the wavelet matrix and the level loop never read it)
+  BCE_TRY(c->text.ensure(c, size_t(n) + 128));
+  BCE_CUDA(c, cudaStreamSynchronize(c->stream));       // idle between calls; orders a fresh buffer's clearing before the copy
+  BCE_CUDA(c, cudaEventRecord(c->ev_prefetch[0], c->h2d_stream));
+  BCE_CUDA(c, cudaMemcpyAsync(c->text.p, T, n, cudaMemcpyHostToDevice, c->h2d_stream));
+  BCE_CUDA(c, cudaEventRecord(c->ev_prefetch[1], c->h2d_stream));
+  c->text_resident = false;
+  c->prefetch_src = T;
+  c->prefetch_n = n;
+  c->prefetch_pending = true;
   return BCE_GPU_OK;
 }
 

@@ -32,6 +32,11 @@ struct Ctx : bce_gpu_ctx {
   size_t total_mem = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t h2d_stream = nullptr;        // bce_gpu_prefetch_input: the next input's upload, beside the level loop
+  cudaEvent_t ev_prefetch[2] = {};
+  const uint8_t* prefetch_src = nullptr;    // what the pending prefetch copies (compared by address and size)
+  uint32_t prefetch_n = 0;
+  bool prefetch_pending = false;
   cudaEvent_t ev[8] = {};
   cudaEvent_t pass_ev[256] = {};     // start/stop pairs around individual radix passes (resolved lazily)
   int pass_ev_n = 0;
@@ -134,6 +139,7 @@ int unbwt_run(Ctx* c, uint32_t offset, uint32_t n, uint8_t* out_host);
 
 // api.cu helpers
 int next_tag(Ctx* c);
+bool is_pinned(const void* p);
 int h2d(Ctx* c, void* dst, const void* src, size_t bytes);
 int d2h(Ctx* c, void* dst, const void* src, size_t bytes);
 int radix_init_device(Ctx* c);   // radix_sort.cu: per-device function attributes

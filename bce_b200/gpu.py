@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "bce_gpu_stage_input", "bce_gpu_front_resident", "bce_gpu_unbwt",
     "bce_gpu_set_emit_mode", "bce_gpu_cse_next_words", "bce_gpu_set_option",
     "bce_gpu_resident_checksum", "bce_gpu_cse_next_buckets", "bce_gpu_host_alloc", "bce_gpu_host_free",
-    "bce_gpu_cse_next_words24",
+    "bce_gpu_cse_next_words24", "bce_gpu_prefetch_input",
 ]
 OPT_EMIT_BATCH_BYTES, OPT_LOCAL_SORT_MIN, OPT_RESIDENT_CHECKSUM, OPT_SLOT_ENTER_NODES = 1, 2, 3, 4
 
@@ -120,6 +120,7 @@ def load_library() -> C.CDLL:
     lib.bce_gpu_set_option.argtypes = [vp, C.c_int, C.c_uint64]
     lib.bce_gpu_cse_next_buckets.argtypes = [vp, C.POINTER(ScanBuckets)]
     lib.bce_gpu_cse_next_words24.argtypes = [vp, C.POINTER(CseWords24)]
+    lib.bce_gpu_prefetch_input.argtypes = [vp, vp, u32]
     lib.bce_gpu_host_alloc.argtypes = [vp, C.c_size_t]
     lib.bce_gpu_host_alloc.restype = vp
     lib.bce_gpu_host_free.argtypes = [vp, vp]
@@ -327,7 +328,12 @@ class Frontend:
             self.set_emit_mode(EMIT_RAW)
         return int(off.value), [int(x) for x in Cv], batches
 
-    def compress_front_discard(self, data, words24: bool = False):
+    def prefetch_input(self, data):
+        """bce_gpu_prefetch_input: upload the next input (page-locked memory) beside the current level loop."""
+        T = _as_u8(data)
+        self._check(self.lib.bce_gpu_prefetch_input(self.h, T.ctypes.data, T.size))
+
+    def compress_front_discard(self, data, words24: bool = False, prefetch_next=None):
         """Same call sequence a consumer makes (fused front end, then batches until done) in the
         context's current emission mode; the batches are left in pinned memory (bench e2e leg).
         Returns (offset, total 32-bit words handed back)."""
@@ -335,6 +341,8 @@ class Frontend:
         off = C.c_uint32()
         Cv = (C.c_uint32 * 8)()
         self._check(self.lib.bce_gpu_compress_front(self.h, T.ctypes.data, T.size, C.byref(off), Cv))
+        if prefetch_next is not None:             # the next input's upload runs beside this input's level loop
+            self.prefetch_input(prefetch_next)
         batch = CseWords24() if words24 else CseWords()
         nxt = self.lib.bce_gpu_cse_next_words24 if words24 else self.lib.bce_gpu_cse_next_words
         total = 0

@@ -204,6 +204,13 @@ int bce_gpu_cse_next_buckets(bce_gpu_ctx *ctx, bce_scan_buckets *out);
 int bce_gpu_compress_front(bce_gpu_ctx *ctx, const uint8_t *T, uint32_t n,
                            uint32_t *offset_out, uint32_t C_out[8]);
 
+/* Start uploading the NEXT input while the level loop of the current one still runs (its batches are being
+ * fetched with bce_gpu_cse_next*): legal once bce_gpu_compress_front / bce_gpu_bwt of the current input has returned
+ * -- the text is not read after the BWT exists.  A following bce_gpu_compress_front / bce_gpu_bwt with the same T
+ * and n finds the text on the device; any other input is uploaded as usual.  T must stay unchanged until then;
+ * only page-locked memory (bce_gpu_host_alloc) can be copied asynchronously, for pageable T this is a no-op. */
+int bce_gpu_prefetch_input(bce_gpu_ctx *ctx, const uint8_t *T, uint32_t n);
+
 /* ---- device-resident variant (measurement) ---------------------------------------
  * stage_input copies T to the device; front_resident then runs stage A + B entirely in
  * HBM (counts are written to device memory, nothing crosses PCIe) and returns the number

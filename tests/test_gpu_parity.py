@@ -129,6 +129,63 @@ def test_resident_matches_hosted(frontend):
         frontend.set_option(OPT_RESIDENT_CHECKSUM, 0)
 
 
+def test_prefetched_input_is_the_input(frontend):
+    """bce_gpu_prefetch_input: the next input's upload started while the current level loop is still being drained.
+    A matching call finds the text on the device, any other input is uploaded as usual; results never depend on it."""
+    import ctypes as C
+
+    from bce_b200 import synth
+    from bce_b200.gpu import CseWords, EMIT_CODER
+    lib, h = frontend.lib, frontend.h
+
+    def pinned(data):
+        p = lib.bce_gpu_host_alloc(h, len(data))
+        assert p
+        C.memmove(p, data, len(data))
+        return p
+
+    A = synth.generate("enwik-shaped", 300_000, 11).tobytes()
+    B = synth.generate("markov2-text", 200_000, 12).tobytes()
+    D = synth.generate("mixed-binary", 150_000, 13).tobytes()
+    pa, pb, pd = pinned(A), pinned(B), pinned(D)
+    try:
+        def run(ptr, n, prefetch=None):
+            frontend.set_emit_mode(EMIT_CODER)
+            off, Cv = C.c_uint32(), (C.c_uint32 * 8)()
+            frontend._check(lib.bce_gpu_compress_front(h, ptr, n, C.byref(off), Cv))
+            if prefetch:
+                frontend._check(lib.bce_gpu_prefetch_input(h, prefetch[0], prefetch[1]))
+            words = [[] for _ in range(8)]
+            b = CseWords()
+            while True:
+                frontend._check(lib.bce_gpu_cse_next_words(h, C.byref(b)))
+                for i in range(8):
+                    if b.count[i]:
+                        words[i].append(np.ctypeslib.as_array((C.c_uint32 * int(b.count[i])).from_address(C.addressof(b.words[i].contents))).copy())
+                if b.done:
+                    break
+            frontend.set_emit_mode(0)
+            return int(off.value), [int(x) for x in Cv], [np.concatenate(w) if w else np.zeros(0, np.uint32) for w in words]
+
+        want = {k: frontend.compress_front_words(v, EMIT_CODER) for k, v in (("A", A), ("B", B), ("D", D))}
+
+        def same(got, key):
+            assert got[0] == want[key][0] and got[1] == want[key][1], key
+            for i in range(8):
+                assert first_diff(got[2][i], want[key][2][i]) is None, (key, i)
+
+        same(run(pa, len(A), prefetch=(pb, len(B))), "A")      # B travels while A's counts are fetched
+        same(run(pb, len(B), prefetch=(pa, len(A))), "B")      # ... and is found on the device; A is prefetched
+        same(run(pd, len(D)), "D")                             # a different input than the one prefetched: uploaded as usual
+        same(run(pa, len(A), prefetch=(pa, len(A))), "A")
+        same(run(pa, len(A)), "A")                             # the same buffer again, prefetched by the call before
+        assert lib.bce_gpu_prefetch_input(h, D, len(D)) == 0   # pageable memory: accepted, nothing happens
+        same(run(pd, len(D)), "D")
+    finally:
+        for p in (pa, pb, pd):
+            lib.bce_gpu_host_free(h, p)
+
+
 def test_three_byte_words_are_the_same_words(frontend):
     """bce_gpu_cse_next_words24: the CODER words of a batch as 3 bytes each (packed on the device before the copy),
     on inputs with many k > 31 counts (three-word escapes) and over several batches."""

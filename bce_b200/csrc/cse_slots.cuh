@@ -27,9 +27,14 @@ namespace bce {
 #ifndef BCE_SL_ITEMS
 #define BCE_SL_ITEMS 4
 #endif
-constexpr int SL_ITEMS = BCE_SL_ITEMS;            // nodes per lane: 4 = 78 registers, 3 CTAs/SM (1 GB: 101 ms); 2 = 64 registers, 4 CTAs/SM (109 ms)
+// nodes per lane x CTAs per SM, big rounds of the 1 GB input (ms): 4 x 4 (64 registers, 40 bytes spilled) 96.2 | 5 x 3: 98.9 |
+// 3 x 4: 100.2 | 4 x 3 (78 registers): 101.0 | 5 x 4: 101.0 | 3 x 3: 109.1 | 2 x 4: 109.3 | 2 x 5: 109.6 | 6 x 2: 113.4
+constexpr int SL_ITEMS = BCE_SL_ITEMS;
 constexpr uint32_t SL_CH = 32 * SL_ITEMS;         // nodes per chunk = places per slot
-constexpr int SL_THREADS = 256, SL_WARPS = SL_THREADS / 32, SL_MINB = SL_ITEMS <= 2 ? 4 : 3;
+#ifndef BCE_SL_MINB
+#define BCE_SL_MINB 4
+#endif
+constexpr int SL_THREADS = 256, SL_WARPS = SL_THREADS / 32, SL_MINB = BCE_SL_MINB;
 
 struct SlotLevel {               // one level's frontier in slot form
   uint32_t n;                    // nodes

@@ -72,7 +72,10 @@ __global__ void __launch_bounds__(256) pack_keys_kernel(const uint8_t* __restric
 // ---------------------------------------------------------------------------------
 constexpr int RR_THREADS = 256;
 constexpr int RR_WARPS = RR_THREADS / 32;
-constexpr int RR_ROWS = 16;                         // rows of 32 consecutive slots per warp
+#ifndef BCE_RR_ROWS
+#define BCE_RR_ROWS 16
+#endif
+constexpr int RR_ROWS = BCE_RR_ROWS;                // rows of 32 consecutive slots per warp
 constexpr int RR_WCHUNK = 32 * RR_ROWS;             // slots per warp
 constexpr int RR_TILE = RR_WARPS * RR_WCHUNK;       // 2048 slots per tile
 

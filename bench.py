@@ -424,7 +424,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         k_ms = radix_ms / k_launches
         note = "sum of CUDA-event pairs around every radix_onesweep_kernel launch of the step"
     else:
-        k_name = "cse_wide_kernel + cse_narrow_kernel (level loop)"
+        k_name = "cse_slots_kernel + cse_wide_kernel + cse_narrow_kernel (level loop)"
         k_launches = max(1, st["cse_launches"])
         k_bytes = (48.0 * st["cse_visits"] + 4.0 * st["cse_words"]) / k_launches
         k_ms = cse_ms / k_launches

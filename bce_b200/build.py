@@ -21,7 +21,7 @@ CSRC = PKG / "csrc"
 HOST = CSRC / "host"
 
 GPU_SOURCES = ["api.cu", "radix_sort.cu", "suffix_sort.cu", "wavelet.cu", "cse.cu", "unbwt.cu"]
-GPU_HEADERS = ["common.cuh", "ctx.h", "cse_wide.cuh", "cse_slots.cuh", "cse_probe.cuh", "local_sort.cuh", "../../include/bce_gpu.h"]
+GPU_HEADERS = ["common.cuh", "ctx.h", "cse_wide.cuh", "cse_slots.cuh", "cse_mid.cuh", "cse_probe.cuh", "local_sort.cuh", "../../include/bce_gpu.h"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

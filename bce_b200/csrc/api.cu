@@ -345,6 +345,12 @@ int bce_gpu_set_option(bce_gpu_ctx* h, int option, uint64_t value) {
     case BCE_GPU_OPT_SLOT_ENTER_NODES:
       c->slot_enter_nodes = value ? value : 2000000;
       return BCE_GPU_OK;
+    case BCE_GPU_OPT_MID_ENTER_NODES:
+      c->mid_enter_nodes = value ? value : 400000;
+      return BCE_GPU_OK;
+    case BCE_GPU_OPT_NO_NARROW_KERNELS:
+      c->no_narrow_kernels = value != 0;
+      return BCE_GPU_OK;
     case BCE_GPU_OPT_RESIDENT_CHECKSUM:
       c->resident_checksum = value != 0;
       return BCE_GPU_OK;

@@ -62,6 +62,9 @@ struct CseDeviceState {
   uint32_t barrier_fail;                 // round at which the grid barrier timed out (+1), 0 = never
   unsigned long long arrivals;           // grid barrier: total CTA arrivals since cse_begin
   unsigned long long barriers;           // grid barriers completed since cse_begin
+#ifdef BCE_GPU_EXPERIMENTS
+  unsigned long long prof[8];            // cse_mid_kernel: SM cycles of CTA 0 per phase of a round, summed
+#endif
 };
 
 struct CseArgs {
@@ -188,7 +191,11 @@ __global__ void cse_init_kernel(CseArgs a, uint32_t n) {
     S->emitted[0][i] = S->emitted[1][i] = 0;
   }
   if (i == 0) { S->visits = 0; S->peak_frontier = 0; S->round = 0; S->status = kCseRunning; S->err = 0;
-                S->barrier_fail = 0; S->arrivals = 0; S->barriers = 0; }
+                S->barrier_fail = 0; S->arrivals = 0; S->barriers = 0;
+#ifdef BCE_GPU_EXPERIMENTS
+                for (int k = 0; k < 8; ++k) S->prof[k] = 0;
+#endif
+  }
 }
 
 __global__ void cse_reset_emitted_kernel(CseDeviceState* S) {
@@ -288,6 +295,7 @@ __device__ __forceinline__ void load_items(const uint32_t* base, uint32_t first,
 
 #include "cse_wide.cuh"   // cse_wide_kernel<ITEMS>: the software-pipelined wide kernel
 #include "cse_slots.cuh"  // cse_slots_kernel: huge frontiers, per-chunk output slots, warps that never wait
+#include "cse_mid.cuh"    // cse_mid_kernel: thousands to half a million nodes per round, one grid barrier per round
 #ifdef BCE_GPU_EXPERIMENTS
 #include "cse_probe.cuh"  // timing probe: one round with fully independent warps
 #endif
@@ -678,6 +686,13 @@ struct CseHost {
   bool in_slots = false;                 // the frontier currently lives in slots (else flat layout)
   const void* slot_fn = nullptr;
   int slot_grid = 0;
+  // frontiers between the cluster kernels' and the wide kernel's: slot layout with redundant scans (cse_mid.cuh)
+  MidArgs mid = {};
+  bool mid_ok = false;
+  const void* mid_fn[3] = {nullptr, nullptr, nullptr};   // 1, 2, 4 nodes per lane
+  int mid_grid = 0;
+  unsigned long long mid_enter = 0;      // frontiers of at most this many nodes go to cse_mid_kernel
+  unsigned long long mid_e0 = 0, mid_e1 = 0;   // ... at most e0: 1 node per lane, at most e1: 2, else 4
 };
 
 static size_t env_size(const char* name, size_t dflt) { return exp_env(name, dflt); }   // experiment builds only
@@ -736,9 +751,28 @@ int cse_begin(Ctx* c, uint32_t n) {
   }
   H->slots_ok = slot_bytes != 0;
   H->in_slots = false;
-  if (want_slots && !H->slots_ok) {          // no room for the slot layout: the flat layout has to hold everything
-    cap = cap_full;
-    while (cap > 4096 && frontier_bytes(cap) > budget / 2) cap = (cap / 2 + 3) & ~size_t(3);
+  // medium frontiers: two arenas of MD_SLOTS slots, double-buffered E-slots and the two directories
+  size_t mid_bytes = 0;
+  H->mid_ok = false;
+  H->mid_enter = std::min<unsigned long long>(c->mid_enter_nodes, mid_max_nodes(4));
+  H->mid_e0 = std::min<unsigned long long>(env_size("BCE_GPU_MID_E0", 96 << 10), mid_max_nodes(1) * 3 / 4);
+  H->mid_e1 = std::min<unsigned long long>(env_size("BCE_GPU_MID_E1", 192 << 10), mid_max_nodes(2) * 3 / 4);
+  if (n >= 8192 && H->mid_enter > 1 && env_size("BCE_GPU_NO_MID", 0) == 0) {
+    const bool raw = a.emit_mode == kEmitRaw;
+    H->mid_fn[0] = raw ? (const void*)cse_mid_kernel<5, 1> : (const void*)cse_mid_kernel<3, 1>;
+    H->mid_fn[1] = raw ? (const void*)cse_mid_kernel<5, 2> : (const void*)cse_mid_kernel<3, 2>;
+    H->mid_fn[2] = raw ? (const void*)cse_mid_kernel<5, 4> : (const void*)cse_mid_kernel<3, 4>;
+    int per_sm = 1;
+    for (const void* fn : H->mid_fn) {
+      int p1 = 0;
+      BCE_CUDA(c, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MidShared))));
+      BCE_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p1, fn, MD_THREADS, sizeof(MidShared)));
+      per_sm = std::min(per_sm, p1);
+    }
+    mid_bytes = Carver::need(6 * MD_PLACES, 4) + Carver::need(2 * size_t(MD_SLOTS), 1) +
+                Carver::need(2 * size_t(MD_TCAP) * 32 * MD_MAX_ITEMS * wmax, 4) + Carver::need(2 * size_t(MD_TCAP), 2) + 4096;
+    if (per_sm < 1 || mid_bytes > left / 2) mid_bytes = 0;
+    else { left -= mid_bytes; H->mid_grid = c->sm_count; }
   }
   H->sets = (c->cse_resident || env_size("BCE_GPU_NO_OVERLAP", 0)) ? 1 : 2;
   // words handed back per batch and stream: small batches let the copy of batch k overlap the
@@ -748,7 +782,7 @@ int cse_begin(Ctx* c, uint32_t n) {
   const size_t per_level_min = (cap + CS_MAX_TILE) * wmax;   // one round must always fit
   if (ew * 8 * 4 * H->sets > left) ew = left / (8 * 4 * H->sets);
   if (ew < per_level_min) ew = per_level_min;
-  const size_t need = frontier_bytes(cap) + desc_bytes + size_t(H->sets) * 8 * Carver::need(ew, 4) + slot_bytes + 4096;
+  const size_t need = frontier_bytes(cap) + desc_bytes + size_t(H->sets) * 8 * Carver::need(ew, 4) + slot_bytes + mid_bytes + 4096;
   BCE_TRY(c->scratch.ensure(c, need));
   Carver cv(c->scratch.p, c->scratch.cap);
   for (int p = 0; p < 2; ++p)
@@ -779,6 +813,14 @@ int cse_begin(Ctx* c, uint32_t n) {
     sl.dir_cap = uint32_t(dir_cap);
     H->slot_grid = slot_grid;
   }
+  if (mid_bytes) {
+    MidArgs& m = H->mid;
+    m.arena = cv.take<uint32_t>(6 * MD_PLACES);
+    m.cnt = cv.take<uint8_t>(2 * size_t(MD_SLOTS));
+    m.eslot = cv.take<uint32_t>(2 * size_t(MD_TCAP) * 32 * MD_MAX_ITEMS * wmax);
+    m.ecnt = cv.take<uint16_t>(2 * size_t(MD_TCAP));
+    H->mid_ok = true;
+  }
   if (!cv.ok()) { set_error(c, "cse_begin: scratch carve failed (need %zu)", need); return BCE_GPU_E_NOMEM; }
   H->ecap_words = ew;
   // per-stream target: the streams are uneven (the largest carries about a third of the words), so a third of the
@@ -796,7 +838,7 @@ int cse_begin(Ctx* c, uint32_t n) {
   a.desc_tiles = uint32_t(desc_tiles);
   a.max_rounds = 0x7FFFFFFFu;
   a.round_limit = uint32_t(std::min<uint64_t>(uint64_t(n) * 8 + 64, 0xFFFFFFF0ull));
-  a.use_narrow = env_size("BCE_GPU_NO_NARROW", 0) ? 0u : 1u;
+  a.use_narrow = (env_size("BCE_GPU_NO_NARROW", 0) || c->no_narrow_kernels) ? 0u : 1u;
   a.dbg = 0;
   a.min_nodes = 0;
   a.max_nodes = ~0ull;
@@ -869,6 +911,7 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
   for (int hops = 0;; ++hops) {
     if (hops > 100000) { set_error(c, "cse: wide/narrow ping-pong"); return BCE_GPU_E_INTERNAL; }
     const bool was_narrow = H->narrow != 0;
+    bool was_mid = false;
     BCE_CUDA(c, cudaEventRecord(c->ev[0], st));
     H->args.max_rounds = 0x7FFFFFFFu;
     H->args.dbg = 0;
@@ -898,6 +941,25 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
       int v;
       int grid;
       const bool use_slots = H->slots_ok && (H->in_slots || H->known_nodes >= kBig);
+      const bool use_mid = H->mid_ok && !use_slots && !H->fixed_items && H->known_nodes <= H->mid_enter;
+      if (use_mid) {
+        // some thousand to half a million nodes per round: slot layout with one grid barrier per round.  The kernel reads
+        // the flat layout in its first round and writes it back when it leaves (kCseGoWide above max_nodes,
+        // kCseGoNarrow for the cluster kernels, batch full, done).
+        grid = H->mid_grid;
+        // the thinner a round, the fewer nodes per lane: a warp alone on its scheduler is bound by its own latencies
+        const int inst = H->known_nodes <= H->mid_e0 ? 0 : H->known_nodes <= H->mid_e1 ? 1 : 2;
+        H->args.max_nodes = mid_max_nodes(1 << inst);                                                    // leaves (kCseGoWide) outside
+        H->args.min_nodes = inst == 0 ? 0 : inst == 1 ? H->mid_e0 * 3 / 4 : H->mid_e1 * 3 / 4;           // [min, max]
+        if (grid != H->last_grid) {
+          if (H->last_grid) { cse_reset_barrier_kernel<<<1, 1, 0, st>>>(H->args.st); c->stats.gpu_launches++; }
+          H->last_grid = grid;
+        }
+        void* kargs[] = {&H->args, &H->mid};
+        BCE_CUDA(c, cudaLaunchCooperativeKernel(H->mid_fn[inst], dim3(grid), dim3(MD_THREADS), kargs, sizeof(MidShared), st));
+        was_mid = true;
+        v = -1;
+      } else
       if (use_slots) {
         // huge frontier: slot layout.  Coming from the flat layout it is converted first and the kernel starts with its
         // scan phase; it comes back (kCseGoWide) when fewer than kLeaveBig nodes are left.
@@ -926,6 +988,7 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
         if (v) H->args.min_nodes = kLeaveBig;
         else {
           H->args.max_nodes = kLeaveSmall;
+          if (H->mid_ok) H->args.min_nodes = H->mid_enter;    // back to cse_mid_kernel once the frontier has shrunk
           // A frontier of a few thousand nodes is a handful of tiles: what a round costs then is the
           // grid barrier, and that grows with the number of CTAs that have to arrive.
           const unsigned long long small_below = env_size("BCE_GPU_CSE_SMALL_NODES", 0);
@@ -970,8 +1033,13 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
       float lms = 0;
       BCE_CUDA(c, cudaEventElapsedTime(&lms, c->ev[0], c->ev[1]));
       if (was_narrow) { c->stats.ms_cse_narrow += lms; c->stats.cse_rounds_narrow += h_state->round - H->last_round; }
-      BCE_TRACE("cse %s kernel: rounds %u..%u status=%u err=%u visits=%llu %.3f ms dbg=%u", was_narrow ? "narrow" : H->in_slots ? "slots" : "wide",
+      BCE_TRACE("cse %s kernel: rounds %u..%u status=%u err=%u visits=%llu %.3f ms dbg=%u", was_narrow ? "narrow" : H->in_slots ? "slots" : was_mid ? "mid" : "wide",
                 H->last_round, h_state->round, h_state->status, h_state->err, h_state->visits, lms, H->args.dbg);
+#ifdef BCE_GPU_EXPERIMENTS
+      if (was_mid)
+        BCE_TRACE("   mid phases (CTA 0, Mcycles): scan %.2f  words %.2f  plan %.2f  round %.2f  sync %.2f  barrier %.2f", h_state->prof[0] / 1e6,
+                  h_state->prof[1] / 1e6, h_state->prof[2] / 1e6, h_state->prof[3] / 1e6, h_state->prof[4] / 1e6, h_state->prof[5] / 1e6);
+#endif
       if (H->args.dbg) { set_error(c, "cse: timing experiment round done (%.3f ms)", lms); return BCE_GPU_E_INTERNAL; }
       H->last_round = h_state->round;
       if (H->in_slots && h_state->status == kCseGoWide && !h_state->err) {

@@ -64,6 +64,8 @@ struct Ctx : bce_gpu_ctx {
   uint32_t local_sort_min = 1u << 20;          // BCE_GPU_OPT_LOCAL_SORT_MIN
   bool resident_checksum = false;              // BCE_GPU_OPT_RESIDENT_CHECKSUM
   uint64_t slot_enter_nodes = 2000000;         // BCE_GPU_OPT_SLOT_ENTER_NODES
+  uint64_t mid_enter_nodes = 400000;           // BCE_GPU_OPT_MID_ENTER_NODES
+  bool no_narrow_kernels = false;              // BCE_GPU_OPT_NO_NARROW_KERNELS
 
   // state of the current input
   uint32_t n = 0;

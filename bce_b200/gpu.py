@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "bce_gpu_cse_next_words24", "bce_gpu_prefetch_input",
 ]
 OPT_EMIT_BATCH_BYTES, OPT_LOCAL_SORT_MIN, OPT_RESIDENT_CHECKSUM, OPT_SLOT_ENTER_NODES = 1, 2, 3, 4
+OPT_MID_ENTER_NODES, OPT_NO_NARROW_KERNELS = 5, 6
 
 
 class BceGpuError(RuntimeError):

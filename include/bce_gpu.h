@@ -105,9 +105,13 @@ int bce_gpu_set_scratch_limit(bce_gpu_ctx *ctx, size_t bytes);
  *                     radix path instead of the tile-local sort (default 2^20)
  *   RESIDENT_CHECKSUM 1 = front_resident also sums the words it emits (see bce_gpu_resident_checksum)
  *   SLOT_ENTER_NODES  the level loop keeps frontiers of at least this many nodes per round in its slot layout
- *                     (default 2,000,000; inputs below 8x this never use it; small values: tests) */
+ *                     (default 2,000,000; inputs below 8x this never use it; small values: tests)
+ *   MID_ENTER_NODES   frontiers of at most this many nodes per round (and more than the cluster kernels take) run in
+ *                     the one-barrier-per-round kernel (default 400,000, at most ~515,000; 1 = never)
+ *   NO_NARROW_KERNELS 1 = the cluster / one-CTA kernels for frontiers of a few thousand nodes are not used (tests:
+ *                     the other kernels then see every frontier size) */
 enum { BCE_GPU_OPT_EMIT_BATCH_BYTES = 1, BCE_GPU_OPT_LOCAL_SORT_MIN = 2, BCE_GPU_OPT_RESIDENT_CHECKSUM = 3,
-       BCE_GPU_OPT_SLOT_ENTER_NODES = 4 };
+       BCE_GPU_OPT_SLOT_ENTER_NODES = 4, BCE_GPU_OPT_MID_ENTER_NODES = 5, BCE_GPU_OPT_NO_NARROW_KERNELS = 6 };
 int bce_gpu_set_option(bce_gpu_ctx *ctx, int option, uint64_t value);
 
 /* Page-locked host memory for the caller's input and output buffers (File::File reads the whole file into one

@@ -242,6 +242,46 @@ def test_slot_layout_forced_on_small_inputs(frontend):
         frontend.set_option(OPT_SLOT_ENTER_NODES, 0)
 
 
+def test_mid_kernel_sees_every_frontier_size(frontend):
+    """Frontiers between the cluster kernels' few thousand nodes and the wide kernel's hundreds of thousands run in
+    cse_mid_kernel (csrc/cse_mid.cuh: slot layout, one grid barrier per round, every CTA scans the slot directory
+    itself, flat layout read on entry and written back on exit).  With the cluster / one-CTA kernels switched off it
+    runs every round from the roots on: every count of every stream (raw), rounds and visits, the packed words'
+    archive, and small batches (the kernel leaves to drain and comes back from the flat layout)."""
+    from bce_b200.gpu import OPT_EMIT_BATCH_BYTES, OPT_NO_NARROW_KERNELS, OPT_MID_ENTER_NODES
+    frontend.set_option(OPT_NO_NARROW_KERNELS, 1)
+    try:
+        used = 0
+        for name, data, _ in small_cases() + medium_cases():
+            if len(data) < 16384:
+                continue
+            Lo, offo, _ = oracle.bwt(data)
+            want = oracle.cse(oracle.wavelet(Lo), len(data))
+            for enter in (0, 3000):                 # default hand-over to the wide kernel, and a very early one (ping-pong)
+                frontend.set_option(OPT_MID_ENTER_NODES, enter)
+                off, Cv, streams = frontend.compress_front(data)
+                st = frontend.stats()
+                assert off == offo and Cv == want["C"], name
+                for i in range(8):
+                    assert first_diff(streams[i], want["streams"][i]) is None, (name, i, enter)
+                assert st["cse_visits"] == sum(want["visits"]) and st["cse_rounds"] == want["rounds"], (name, enter)
+            frontend.set_option(OPT_MID_ENTER_NODES, 0)
+            assert host.compress(frontend, data, threads=1) == oracle.compress(data), name
+            frontend.set_option(OPT_EMIT_BATCH_BYTES, 1 << 18)
+            try:
+                _, streams2 = frontend.cse(Lo)
+                assert frontend.last_batches > 1
+            finally:
+                frontend.set_option(OPT_EMIT_BATCH_BYTES, 0)
+            for i in range(8):
+                assert first_diff(streams2[i], want["streams"][i]) is None, (name, i, "batched")
+            used += 1
+        assert used >= 5
+    finally:
+        frontend.set_option(OPT_NO_NARROW_KERNELS, 0)
+        frontend.set_option(OPT_MID_ENTER_NODES, 0)
+
+
 def test_scan_buckets_from_the_device(frontend):
     """bce_gpu_cse_next_buckets: per stream and (k, key) the device's runs of symbol bytes, joined over
     the batches, are the stream's SCAN words of that bucket in order; keys first appear in stream order; the

@@ -277,6 +277,39 @@ __device__ __forceinline__ uint32_t lookback_warp_wide(uint64_t* desc, uint32_t 
   return lookback_resolve_wide<B>(desc, tile, first, tag, agg, err);
 }
 
+// The same for blocks of many warps in latency-bound kernels: the warp totals are scanned by shuffles in every warp
+// (one shared load per lane instead of a walk over all of them), and a warp whose threads all hold zero -- `active`
+// false, not the first warp -- only keeps the barriers company (its return value and `total` are then undefined).
+template <class T, int THREADS>
+__device__ __forceinline__ T block_exclusive_scan_sparse(T v, T* scratch, T& total, bool active) {
+  constexpr int NW = THREADS / 32;
+  const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+  T inc = v;
+  if (active) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      T o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= unsigned(d)) inc += o;
+    }
+  }
+  if (lane == 31) scratch[warp] = active ? inc : T(0);
+  __syncthreads();
+  T woff = 0;
+  if (active) {
+    T winc = lane < unsigned(NW) ? scratch[lane] : T(0);
+#pragma unroll
+    for (int d = 1; d < NW; d <<= 1) {
+      T o = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= unsigned(d)) winc += o;
+    }
+    total = __shfl_sync(0xffffffffu, winc, NW - 1);
+    const T before = __shfl_sync(0xffffffffu, winc, warp ? warp - 1 : 0);
+    woff = warp ? before : T(0);
+  }
+  __syncthreads();          // scratch may be reused right after
+  return woff + inc - v;
+}
+
 // Block-wide exclusive scan of one value per thread (THREADS multiple of 32, <= 1024).
 // `total` receives the block sum.  Uses (THREADS/32) words of shared scratch.
 template <class T, int THREADS>

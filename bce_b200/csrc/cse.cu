@@ -350,34 +350,22 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(THREADS, 1) cse_narr
       sh.all_emitted[0][tid] = S->emitted[gpar][tid];
     }
   }
-  unsigned long long cursor = S->emitted[gpar][l];
   unsigned long long visits = 0, peak = 0;
   int p = 0;
   cluster.sync();                                    // nobody writes into a CTA that is still loading
+#ifdef BCE_GPU_EXPERIMENTS
+  long long stamp_ = clock64();
+  unsigned long long prof_[5] = {0, 0, 0, 0, 0};     // (registers: a stamp costs two instructions, not a trip to memory)
+#define NARROW_STAMP(i) do { const long long now_ = clock64(); prof_[i] += (unsigned long long)(now_ - stamp_); stamp_ = now_; } while (0)
+#else
+#define NARROW_STAMP(i) do { } while (0)
+#endif
 
   uint32_t status;
   for (;;) {
-    if (tid == 0) {
-      uint32_t total = 0, widest = 0, drain = 0;
-      for (int k = 0; k < 8; ++k) {
-        const uint32_t cnt = sh.all_cnt[p][k];
-        total += cnt;
-        widest = max(widest, cnt);
-        if (sh.all_emitted[p][k] + (unsigned long long)cnt * maxw > a.ecap[k] || sh.all_emitted[p][k] >= a.esoft[k]) drain = 1;
-      }
-      sh.decision = total == 0 ? kCseDone
-                  : round >= a.round_limit ? kCseRunaway
-                  : widest > CAP / 2 ? kCseGoWide                   // a node has <= 2 children: the next round always fits
-                  : (K > 1 && widest <= kNarrowEnter) ? kCseGoNarrow   // the one-node-per-thread instance is quicker there
-                  : (K == 1 && a.use_tiny && widest <= a.tiny_enter) ? kCseGoNarrow   // and the one-CTA kernel for a handful of nodes
-                  : drain ? kCseDrain : kCseRunning;
-      if (sh.decision == kCseRunning) { visits += total; peak = max(peak, (unsigned long long)total); }
-    }
-    __syncthreads();
-    status = sh.decision;
-    if (status != kCseRunning) break;
-
-    const uint32_t cnt = sh.cz[p] + sh.co[p];
+    const uint32_t cnt = min(sh.cz[p] + sh.co[p], CAP);
+    const unsigned long long cursor = sh.all_emitted[p][l];      // this level's words so far (every CTA holds all eight)
+    const unsigned warp_of_tid = tid >> 5;
     uint32_t s[K], x0[K], x1[K];
     uint64_t wa[K], wb[K], wc[K];
 #pragma unroll
@@ -396,6 +384,38 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(THREADS, 1) cse_narr
         wc[j] = __ldg(R + ((s[j] + x0[j]) >> 5));
       } else { wa[j] = wb[j] = wc[j] = 0; }
     }
+    // the decision about this round is taken while its rank words are on their way (a round that is not run has
+    // loaded them for nothing: cnt <= CAP nodes of the shared frontier are always valid)
+    if (tid < 32) {                                  // lanes 0..7 look at a level each (the same in every CTA of the cluster)
+      const int k = tid & 7;
+      const uint32_t cntk = sh.all_cnt[p][k];
+      unsigned long long ecap_k = 0, esoft_k = 0;     // (selected, not indexed: the arguments stay in the constant bank)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (k == j) { ecap_k = a.ecap[j]; esoft_k = a.esoft[j]; }
+      const unsigned long long em_k = sh.all_emitted[p][k];
+      const bool dr = em_k + (unsigned long long)cntk * maxw > ecap_k || em_k >= esoft_k;
+      const bool drain = (__ballot_sync(0xffffffffu, dr) & 0xFFu) != 0;
+      uint32_t total = cntk, widest = cntk;
+#pragma unroll
+      for (int d = 1; d < 8; d <<= 1) {
+        total += __shfl_xor_sync(0xffffffffu, total, d);
+        widest = max(widest, __shfl_xor_sync(0xffffffffu, widest, d));
+      }
+      if (tid == 0) {
+        sh.decision = total == 0 ? kCseDone
+                    : round >= a.round_limit ? kCseRunaway
+                    : widest > CAP / 2 ? kCseGoWide                   // a node has <= 2 children: the next round always fits
+                    : (K > 1 && widest <= kNarrowEnter) ? kCseGoNarrow   // the one-node-per-thread instance is quicker there
+                    : (K == 1 && a.use_tiny && widest <= a.tiny_enter) ? kCseGoNarrow   // and the one-CTA kernel for a handful of nodes
+                    : drain ? kCseDrain : kCseRunning;
+        if (sh.decision == kCseRunning) { visits += total; peak = max(peak, (unsigned long long)total); }
+      }
+    }
+    __syncthreads();
+    status = sh.decision;
+    if (status != kCseRunning) break;
+    NARROW_STAMP(0);
+
     uint32_t fz = 0, fo = 0, nwsum = 0;
     uint32_t cs0[K], ca[K], cb[K], cs1[K], oa[K], ob[K];       // zero-child and one-child of every node
     uint32_t e0[K], e1[K], e2[K], nw[K];
@@ -424,9 +444,12 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(THREADS, 1) cse_narr
         nwsum += nw[j];
       }
     }
+    NARROW_STAMP(1);
     const uint64_t mine = uint64_t(__popc(fz)) | (uint64_t(__popc(fo)) << 21) | (uint64_t(nwsum) << 42);
     uint64_t tot;
-    const uint64_t excl = block_exclusive_scan<uint64_t, THREADS>(mine, sh.scan, tot);
+    const bool scan_active = warp_of_tid == 0 || warp_of_tid * 32u * K < cnt;      // other warps hold no node: zeros
+    const uint64_t excl = block_exclusive_scan_sparse<uint64_t, THREADS>(mine, sh.scan, tot, scan_active);
+    NARROW_STAMP(2);
     const uint32_t tz = uint32_t(tot) & 0x1FFFFFu, to = uint32_t(tot >> 21) & 0x1FFFFFu, te = uint32_t(tot >> 42) & 0x1FFFFFu;
     const int q = p ^ 1;
     // the next level's CTA receives its frontier directly in its shared memory
@@ -447,16 +470,17 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(THREADS, 1) cse_narr
         if (fo >> j & 1u) { rs[oat] = cs1[j]; ra[oat] = oa[j]; rb[oat] = ob[j]; ++oat; }
       }
     }
-    cursor += te;
     if (tid == 0) {
       *cluster.map_shared_rank(&sh.cz[q], ln) = tz;
       *cluster.map_shared_rank(&sh.co[q], ln) = to;
     }
     if (tid < 8) {            // all-gather: level ln's next size and this level's cursor, to every CTA
       cluster.map_shared_rank(&sh.all_cnt[q][0], tid)[ln] = tz + to;
-      cluster.map_shared_rank(&sh.all_emitted[q][0], tid)[l] = cursor;
+      cluster.map_shared_rank(&sh.all_emitted[q][0], tid)[l] = cursor + te;
     }
+    NARROW_STAMP(3);
     cluster.sync();
+    NARROW_STAMP(4);
     p = q;
     ++round;
   }
@@ -474,12 +498,15 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(THREADS, 1) cse_narr
     if (tid == 0) {
       S->cnt[opar][l][0] = cz;
       S->cnt[opar][l][1] = co;
-      S->emitted[opar][l] = cursor;
+      S->emitted[opar][l] = sh.all_emitted[p][l];
       if (l == 0) {
         S->round = round;
         S->status = status;
         S->visits += visits;
         if (peak > S->peak_frontier) S->peak_frontier = peak;
+#ifdef BCE_GPU_EXPERIMENTS
+        for (int k = 0; k < 5; ++k) S->prof[k] += prof_[k];
+#endif
       }
     }
   }
@@ -1036,9 +1063,15 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
       BCE_TRACE("cse %s kernel: rounds %u..%u status=%u err=%u visits=%llu %.3f ms dbg=%u", was_narrow ? "narrow" : H->in_slots ? "slots" : was_mid ? "mid" : "wide",
                 H->last_round, h_state->round, h_state->status, h_state->err, h_state->visits, lms, H->args.dbg);
 #ifdef BCE_GPU_EXPERIMENTS
-      if (was_mid)
-        BCE_TRACE("   mid phases (CTA 0, Mcycles): scan %.2f  words %.2f  plan %.2f  round %.2f  sync %.2f  barrier %.2f", h_state->prof[0] / 1e6,
-                  h_state->prof[1] / 1e6, h_state->prof[2] / 1e6, h_state->prof[3] / 1e6, h_state->prof[4] / 1e6, h_state->prof[5] / 1e6);
+      {
+        static unsigned long long prev[8] = {};
+        if (h_state->prof[0] < prev[0]) for (auto& v : prev) v = 0;     // a new run started the sums again
+        const uint32_t nr = std::max(1u, h_state->round - H->last_round);
+        BCE_TRACE("   phases (CTA 0, cycles per round): %.0f %.0f %.0f %.0f %.0f %.0f", double(h_state->prof[0] - prev[0]) / nr,
+                  double(h_state->prof[1] - prev[1]) / nr, double(h_state->prof[2] - prev[2]) / nr, double(h_state->prof[3] - prev[3]) / nr,
+                  double(h_state->prof[4] - prev[4]) / nr, double(h_state->prof[5] - prev[5]) / nr);
+        for (int k = 0; k < 8; ++k) prev[k] = h_state->prof[k];
+      }
 #endif
       if (H->args.dbg) { set_error(c, "cse: timing experiment round done (%.3f ms)", lms); return BCE_GPU_E_INTERNAL; }
       H->last_round = h_state->round;

@@ -195,7 +195,10 @@ __global__ void __launch_bounds__(MD_THREADS, 1) cse_mid_kernel(CseArgs a, MidAr
         const uint32_t o1 = __shfl_up_sync(0xffffffffu, tin, d), o2 = __shfl_up_sync(0xffffffffu, sin, d);
         if (l >= d) { tin += o1; sin += o2; }
       }
-      const bool drain = em + (unsigned long long)nl * max_words(a) > a.ecap[l] || em >= a.esoft[l];
+      unsigned long long ecap_l = 0, esoft_l = 0;     // (selected, not indexed: the arguments stay in the constant bank)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) if (l == j) { ecap_l = a.ecap[j]; esoft_l = a.esoft[j]; }
+      const bool drain = em + (unsigned long long)nl * max_words(a) > ecap_l || em >= esoft_l;
       const unsigned m8 = 0xFFu;
       const bool any_drain = (__ballot_sync(0xffffffffu, drain) & m8) != 0;
       const bool too_wide = (__ballot_sync(0xffffffffu, nl > a.cap) & m8) != 0;

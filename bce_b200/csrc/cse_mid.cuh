@@ -48,7 +48,8 @@ struct MidShared {
   uint32_t P[16 * (MD_THREADS + 1)];   // [mid_pidx(c)] nodes of the level before slot c (a level's slots are consecutive)
   uint32_t PE[8 * (MD_THREADS + 1)];   // [mid_eidx(t)] words of the level before the E-slot of chunk t (previous round)
   uint16_t start[MD_SLOTS];        // [doff[l] + q] = slot holding position q * chunk size of level l
-  uint64_t ex[MD_THREADS + 1];     // exclusive scan over the threads: low = nodes, high = words
+  uint64_t ex[MD_THREADS + 1];     // exclusive scan over the threads: low = nodes, high = words (read through mid_ex)
+  uint32_t ex_valid;               // threads (a multiple of 32) whose ex[] entry was written this round; the others' = total
   uint64_t scan[MD_WARPS];
   uint32_t n[8], nz[8];            // this round's frontier: nodes per level, of which zero-children
   uint32_t doff[9];                // first slot number of every level (parity cur); the level has 2 * sz[l] slots
@@ -60,6 +61,8 @@ struct MidShared {
   unsigned long long ebase[8];     // ... where the previous round's words start
   uint32_t decision;
 };
+
+__device__ __forceinline__ uint64_t mid_ex(const MidShared& sh, uint32_t i) { return sh.ex[i < max(sh.ex_valid, 32u) ? i : MD_THREADS]; }
 
 // slot and offset of the ITEMS positions a lane holds in chunk q of level l, from the shared directory
 template <int ITEMS>
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(MD_THREADS, 1) cse_mid_kernel(CseArgs a, MidAr
     sh.emitted[tid] = sh.ebase[tid] = vol_load64(&S->emitted[par][tid]);
   }
   if (tid < 9) { sh.doff[tid] = 0; sh.ptfirst[tid] = 0; }
+  if (tid == 0) sh.ex_valid = 0;
   __syncthreads();
 
   for (;;) {
@@ -164,9 +168,12 @@ __global__ void __launch_bounds__(MD_THREADS, 1) cse_mid_kernel(CseArgs a, MidAr
       uint32_t esum = 0;
 #pragma unroll
       for (int w = 0; w < 4; ++w) esum += (eb[w] & 0xFFFFu) + (eb[w] >> 16);
+      // warps whose slots and chunks all lie beyond this round's hold zeros: they skip the scan, and their threads'
+      // entries of ex[] read as the total (mid_ex)
       uint64_t tot;
-      const uint64_t excl = block_exclusive_scan<uint64_t, MD_THREADS>((uint64_t(esum) << 32) | csum, sh.scan, tot);
-      sh.ex[tid] = excl;
+      const uint64_t excl = block_exclusive_scan_sparse<uint64_t, MD_THREADS>((uint64_t(esum) << 32) | csum, sh.scan, tot,
+                                                                             warp == 0 || tid < sh.ex_valid);
+      if (warp == 0 || tid < sh.ex_valid) sh.ex[tid] = excl;
       if (tid == 0) sh.ex[MD_THREADS] = tot;
       __syncthreads();
       // (the plan below needs only ex[]: the last warp makes it -- its slots are beyond those of all but the widest
@@ -180,9 +187,9 @@ __global__ void __launch_bounds__(MD_THREADS, 1) cse_mid_kernel(CseArgs a, MidAr
       uint32_t nl = sh.n[l], nzl = sh.nz[l];
       unsigned long long em = sh.emitted[l];
       if (!from_flat) {
-        nl = uint32_t(sh.ex[sh.doff[l + 1] / 16u]) - uint32_t(sh.ex[sh.doff[l] / 16u]);
+        nl = uint32_t(mid_ex(sh, sh.doff[l + 1] / 16u)) - uint32_t(mid_ex(sh, sh.doff[l] / 16u));
         nzl = 0;                                      // (set by the thread that scans the first O-slot, below)
-        const uint32_t words = uint32_t(sh.ex[sh.ptfirst[l + 1] / 8u] >> 32) - uint32_t(sh.ex[sh.ptfirst[l] / 8u] >> 32);
+        const uint32_t words = uint32_t(mid_ex(sh, sh.ptfirst[l + 1] / 8u) >> 32) - uint32_t(mid_ex(sh, sh.ptfirst[l] / 8u) >> 32);
         if (lane < 8) sh.ebase[l] = em;               // the previous round's words start here ...
         em += words;                                  // ... and this round's behind them
       }
@@ -235,9 +242,9 @@ __global__ void __launch_bounds__(MD_THREADS, 1) cse_mid_kernel(CseArgs a, MidAr
 #pragma unroll
       for (int k = 1; k < 8; ++k) { L += s0 >= sh.doff[k] ? 1 : 0; LE += t0 >= sh.ptfirst[k] ? 1 : 0; }
       const uint32_t lvl_first = sh.doff[L], first_o = lvl_first + sh.sz[L];
-      const uint64_t excl = sh.ex[tid];
+      const uint64_t excl = mid_ex(sh, tid);
       if (s0 < lvl_first + 2u * sh.sz[L]) {           // (entries beyond a level's slots are never read)
-        uint32_t run = uint32_t(excl) - uint32_t(sh.ex[lvl_first / 16u]);
+        uint32_t run = uint32_t(excl) - uint32_t(mid_ex(sh, lvl_first / 16u));
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           const uint32_t ck = (cb[k >> 2] >> (8 * (k & 3))) & 255u;
@@ -251,7 +258,7 @@ __global__ void __launch_bounds__(MD_THREADS, 1) cse_mid_kernel(CseArgs a, MidAr
         }
       }
       if (t0 < sh.ptfirst[LE] + sh.pnch[LE]) {
-        uint32_t erun = uint32_t(excl >> 32) - uint32_t(sh.ex[sh.ptfirst[LE] / 8u] >> 32);
+        uint32_t erun = uint32_t(excl >> 32) - uint32_t(mid_ex(sh, sh.ptfirst[LE] / 8u) >> 32);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           sh.PE[k * (MD_THREADS + 1) + tid] = erun;   // = mid_eidx(t0 + k)
@@ -442,6 +449,8 @@ __global__ void __launch_bounds__(MD_THREADS, 1) cse_mid_kernel(CseArgs a, MidAr
       sh.pnch[tid] = sh.nch[tid];
     }
     if (tid < 9) { sh.doff[tid] = sh.ndoff[tid]; sh.ptfirst[tid] = sh.tfirst[tid]; }
+    if (tid == 0)       // threads that will hold slots (16 each) or chunks (8 each) of the next round, rounded up to warps
+      sh.ex_valid = (max((sh.ndoff[8] + 15u) / 16u, (sh.tfirst[8] + 7u) / 8u) + 31u) & ~31u;
     MID_STAMP(4);
     const bool ok = grid_barrier(S, barrier_no++, round);
     MID_STAMP(5);

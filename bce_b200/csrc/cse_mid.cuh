@@ -6,7 +6,7 @@
 // -> rank words -> tile aggregates -> chained scan -> stores -> grid barrier); cse_slots_kernel needs three grid
 // barriers per round for its distributed scans.
 //
-// How.  The slot layout of cse_slots.cuh (a chunk of MD_CH nodes writes its zero-children, its one-children and its
+// How.  The slot layout of cse_slots.cuh (a chunk of 32 / 64 / 128 nodes writes its zero-children, its one-children and its
 // emitted words into slots it owns, so no output position depends on another warp) with the scans made REDUNDANT:
 // a round's directory is a byte per slot -- at most 8 K slots here -- so after the single grid barrier of a round
 // every CTA reads the whole directory (one 16-byte load per thread), scans it in shared memory and knows what every

@@ -782,8 +782,9 @@ int cse_begin(Ctx* c, uint32_t n) {
   size_t mid_bytes = 0;
   H->mid_ok = false;
   H->mid_enter = std::min<unsigned long long>(c->mid_enter_nodes, mid_max_nodes(4));
-  H->mid_e0 = std::min<unsigned long long>(env_size("BCE_GPU_MID_E0", 96 << 10), mid_max_nodes(1) * 3 / 4);
-  H->mid_e1 = std::min<unsigned long long>(env_size("BCE_GPU_MID_E1", 192 << 10), mid_max_nodes(2) * 3 / 4);
+  // (a small MID_ENTER_NODES -- tests -- scales the instance thresholds down with it, so that all three instances run)
+  H->mid_e0 = std::min<unsigned long long>({env_size("BCE_GPU_MID_E0", 96 << 10), mid_max_nodes(1) * 3 / 4, H->mid_enter / 4});
+  H->mid_e1 = std::min<unsigned long long>({env_size("BCE_GPU_MID_E1", 192 << 10), mid_max_nodes(2) * 3 / 4, H->mid_enter / 2});
   if (n >= 8192 && H->mid_enter > 1 && env_size("BCE_GPU_NO_MID", 0) == 0) {
     const bool raw = a.emit_mode == kEmitRaw;
     H->mid_fn[0] = raw ? (const void*)cse_mid_kernel<5, 1> : (const void*)cse_mid_kernel<3, 1>;

@@ -422,9 +422,9 @@ int bce_gpu_cse_begin(bce_gpu_ctx* h, const uint8_t* L, uint32_t n, uint32_t C_o
   return BCE_GPU_OK;
 }
 
-static int next_words(Ctx* c, bce::CseWordBatch* wb, bool pack24 = false) {
+static int next_words(Ctx* c, bce::CseWordBatch* wb, bool pack20 = false) {
   const auto t0 = std::chrono::steady_clock::now();
-  BCE_TRY(bce::cse_advance(c, false, wb, pack24));
+  BCE_TRY(bce::cse_advance(c, false, wb, pack20));
   c->stats.ms_cse_total += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
   return BCE_GPU_OK;
 }
@@ -458,12 +458,12 @@ int bce_gpu_cse_next_words(bce_gpu_ctx* h, bce_cse_words* out) {
   return BCE_GPU_OK;
 }
 
-int bce_gpu_cse_next_words24(bce_gpu_ctx* h, bce_cse_words24* out) {
+int bce_gpu_cse_next_words20(bce_gpu_ctx* h, bce_cse_words20* out) {
   if (!h || !out) return BCE_GPU_E_ARG;
   Ctx* c = static_cast<Ctx*>(h);
   bce::begin_call(c);
   if (!c->cse_active || c->cse_emit_mode_active != BCE_EMIT_CODER) {
-    bce::set_error(c, "cse_next_words24: needs a run started in BCE_EMIT_CODER mode");
+    bce::set_error(c, "cse_next_words20: needs a run started in BCE_EMIT_CODER mode");
     return BCE_GPU_E_STATE;
   }
   bce::CseWordBatch wb;

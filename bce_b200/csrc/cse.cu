@@ -20,10 +20,11 @@
 //
 // Emission is word based.  Raw mode writes the five arguments of set() (20 B, bce_tuple);
 // the packed modes write what the host coder actually consumes (one word; three when k > 31):
-//   coder  [esc:1 @23|ctx:10 @10|k:5 @5|sym:5]   ctx = get_context index, bce.cpp:671-677, for the
-//          stream's configured context bits; esc: k > 31 was halved nb times (bce.cpp:507-510), two
-//          more words carry nb and the nb low bits of the symbol: [low[0..19) @5|nb:5], [low >> 19].
-//          Every word is below 2^24, so a batch crosses PCIe as 3 bytes per word (cse_pack24_kernel)
+//   coder  [ctx:10 @10|k:5 @5|sym:5]   ctx = get_context index, bce.cpp:671-677, for the stream's configured
+//          context bits.  k > 31 was halved nb times (bce.cpp:507-510): the word's k field is 0 then (a count's k
+//          is at least 2) and two more words follow, [low[0..10) @10|nb:5 @5|k:5] and [low >> 10], with k, nb and
+//          the nb low bits of the symbol.  Every word is below 2^20, so a batch crosses PCIe as 2.5 bytes per word
+//          (cse_pack20_kernel)
 //   scan   [esc:1|nb:5 @26|q2:8 @18|q1:8 @10|k:5 @5|sym:5]   ScanCoder::set, bce.cpp:737-744
 //
 // Algorithmic HBM bytes: 48 B per node visit + 20 B per emitted count.
@@ -119,9 +120,9 @@ __device__ __forceinline__ uint32_t count_words(const CseArgs& a, int level, uin
     const uint32_t w = (ctx << 10) | (k << 5) | s;
     if (nb == 0) { e0 = w; e1 = e2 = 0; return 1u; }
     const uint32_t low = sym & ((1u << nb) - 1u);                                  // nb <= 27
-    e0 = 0x800000u | w;
-    e1 = nb | ((low & 0x7FFFFu) << 5);
-    e2 = low >> 19;
+    e0 = (ctx << 10) | s;                                                         // k field 0: two more words
+    e1 = k | (nb << 5) | ((low & 0x3FFu) << 10);
+    e2 = low >> 10;
     return 3u;
   }
   while (k > 31u) { k = (k >> 1) + (~s & 1u); s >>= 1; ++nb; }                   // bce.cpp:738-741
@@ -221,24 +222,27 @@ __global__ void __launch_bounds__(256) cse_checksum_kernel(const uint32_t* __res
   if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], s); atomicAdd(&acc[1], ws); }
 }
 
-// Words below 2^24 leave as 3 bytes each: a thread turns 4 words into 12 bytes (three aligned 32-bit stores).
-__global__ void __launch_bounds__(256) cse_pack24_kernel(const uint32_t* __restrict__ words, unsigned long long count,
+// Words below 2^20 leave as 20 bits each: a thread turns 8 words into 20 bytes (five aligned 32-bit stores).
+__global__ void __launch_bounds__(256) cse_pack20_kernel(const uint32_t* __restrict__ words, unsigned long long count,
                                                          uint32_t* __restrict__ out) {
-  const unsigned long long quads = (count + 3) / 4;
-  for (unsigned long long q = blockIdx.x * 256ull + threadIdx.x; q < quads; q += gridDim.x * 256ull) {
-    const unsigned long long j = 4 * q;
-    uint32_t w0, w1 = 0, w2 = 0, w3 = 0;
-    if (j + 4 <= count) {
-      const uint4 v = *reinterpret_cast<const uint4*>(words + j);          // emission buffers are 256-byte aligned
-      w0 = v.x; w1 = v.y; w2 = v.z; w3 = v.w;
+  const unsigned long long groups = (count + 7) / 8;
+  for (unsigned long long q = blockIdx.x * 256ull + threadIdx.x; q < groups; q += gridDim.x * 256ull) {
+    const unsigned long long j = 8 * q;
+    uint32_t a[8];
+    if (j + 8 <= count) {
+      const uint4 v0 = *reinterpret_cast<const uint4*>(words + j);         // emission buffers are 256-byte aligned
+      const uint4 v1 = *reinterpret_cast<const uint4*>(words + j + 4);
+      a[0] = v0.x; a[1] = v0.y; a[2] = v0.z; a[3] = v0.w; a[4] = v1.x; a[5] = v1.y; a[6] = v1.z; a[7] = v1.w;
     } else {
-      w0 = words[j];
-      if (j + 1 < count) w1 = words[j + 1];
-      if (j + 2 < count) w2 = words[j + 2];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = j + k < count ? words[j + k] : 0u;
     }
-    out[3 * q] = w0 | (w1 << 24);
-    out[3 * q + 1] = (w1 >> 8) | (w2 << 16);
-    out[3 * q + 2] = (w2 >> 16) | (w3 << 8);
+    uint32_t* o = out + 5 * q;                                             // word k of the group sits at bit 20 k
+    o[0] = a[0] | (a[1] << 20);
+    o[1] = (a[1] >> 12) | (a[2] << 8) | (a[3] << 28);
+    o[2] = (a[3] >> 4) | (a[4] << 16);
+    o[3] = (a[4] >> 16) | (a[5] << 4) | (a[6] << 24);
+    o[4] = (a[6] >> 8) | (a[7] << 12);
   }
 }
 
@@ -1188,7 +1192,7 @@ static int run_batch(Ctx* c, int set, size_t cnt[8], bool* done) {
 // One batch of emitted words.  resident: counts stay in device memory (measurement), the
 // whole loop runs here.  Otherwise a batch is copied to pinned host memory on the copy stream
 // while the kernels already fill the other buffer set with the next batch.
-int cse_advance(Ctx* c, bool resident, CseWordBatch* out, bool pack24) {
+int cse_advance(Ctx* c, bool resident, CseWordBatch* out, bool pack20) {
   if (!c->cse_active || !c->cse) { set_error(c, "cse_next without cse_begin"); return BCE_GPU_E_STATE; }
   CseHost* H = c->cse;
   if (out) memset(out, 0, sizeof *out);
@@ -1210,28 +1214,27 @@ int cse_advance(Ctx* c, bool resident, CseWordBatch* out, bool pack24) {
     if (H->sets == 2) H->fill_set ^= 1;
   }
   // copy the pending batch out on the copy stream ...
-  if (pack24 && H->args.emit_mode != kEmitCoder) { set_error(c, "24-bit words need BCE_EMIT_CODER"); return BCE_GPU_E_STATE; }
-  const size_t unit = pack24 ? 3 : 4;                   // bytes per word on the host side
+  if (pack20 && H->args.emit_mode != kEmitCoder) { set_error(c, "20-bit words need BCE_EMIT_CODER"); return BCE_GPU_E_STATE; }
   size_t bytes = 64, at_b[8];
-  for (int l = 0; l < 8; ++l) {                           // the pack kernel writes whole groups of 4 words = 12 bytes
-    at_b[l] = bytes;
-    bytes += ((pack24 ? (H->pending_cnt[l] + 3) / 4 * 12 : H->pending_cnt[l] * unit) + 15) & ~size_t(15);
+  for (int l = 0; l < 8; ++l) {                           // the pack kernel writes whole groups of 8 words = 20 bytes
+    at_b[l] = bytes;                                      // (+ 16: the host reads 8 bytes at a time)
+    bytes += ((pack20 ? (H->pending_cnt[l] + 7) / 8 * 20 + 16 : H->pending_cnt[l] * 4) + 15) & ~size_t(15);
   }
   PinnedBuf& pin = H->pinned_flip ? c->pinned_emit2 : c->pinned_emit;
   H->pinned_flip ^= 1;
   BCE_TRY(pin.ensure(c, bytes));
   char* hp = pin.as<char>();
-  if (pack24) BCE_TRY(c->pack_tmp.ensure(c, bytes));
+  if (pack20) BCE_TRY(c->pack_tmp.ensure(c, bytes));
   cudaStream_t cs = c->copy_stream;
-  if (pack24) {
+  if (pack20) {
     // Packed on the compute stream, before the next batch's kernels: those are persistent and hold every SM, a pack
     // kernel on the copy stream would wait for them and the copy with it (measured: e2e 326 -> 360 ms).  ~0.5 ms per GB.
     for (int l = 0; l < 8; ++l) {
       if (!H->pending_cnt[l]) continue;
       uint32_t* pk = reinterpret_cast<uint32_t*>(c->pack_tmp.as<char>() + at_b[l]);
-      const size_t quads = (H->pending_cnt[l] + 3) / 4;
-      const int grid = int(std::min<size_t>((quads + 255) / 256, size_t(c->sm_count) * 8));
-      cse_pack24_kernel<<<grid, 256, 0, c->stream>>>(H->emit_dev[H->pending_set][l], H->pending_cnt[l], pk);
+      const size_t groups = (H->pending_cnt[l] + 7) / 8;
+      const int grid = int(std::min<size_t>((groups + 255) / 256, size_t(c->sm_count) * 8));
+      cse_pack20_kernel<<<grid, 256, 0, c->stream>>>(H->emit_dev[H->pending_set][l], H->pending_cnt[l], pk);
       c->stats.gpu_launches++;
     }
     BCE_CUDA(c, cudaGetLastError());
@@ -1243,8 +1246,8 @@ int cse_advance(Ctx* c, bool resident, CseWordBatch* out, bool pack24) {
     out->words[l] = reinterpret_cast<const uint32_t*>(hp + at_b[l]);
     out->count[l] = H->pending_cnt[l];
     if (!H->pending_cnt[l]) continue;
-    if (pack24)
-      BCE_CUDA(c, cudaMemcpyAsync(hp + at_b[l], c->pack_tmp.as<char>() + at_b[l], H->pending_cnt[l] * 3, cudaMemcpyDeviceToHost, cs));
+    if (pack20)
+      BCE_CUDA(c, cudaMemcpyAsync(hp + at_b[l], c->pack_tmp.as<char>() + at_b[l], (H->pending_cnt[l] * 5 + 1) / 2, cudaMemcpyDeviceToHost, cs));
     else
       BCE_CUDA(c, cudaMemcpyAsync(hp + at_b[l], H->emit_dev[H->pending_set][l], H->pending_cnt[l] * sizeof(uint32_t),
                                   cudaMemcpyDeviceToHost, cs));

@@ -55,7 +55,7 @@ struct Ctx : bce_gpu_ctx {
   PinnedBuf pinned_emit2;
   PinnedBuf pinned_io;      // staging for pageable caller buffers
   DevBuf scan_tmp;          // bce -s: sort buffers, bucketed symbols and bucket tables of one batch
-  DevBuf pack_tmp;          // a batch's words as 3 bytes each, on their way to the host (bce_gpu_cse_next_words24)
+  DevBuf pack_tmp;          // a batch's words as 20 bits each, on their way to the host (bce_gpu_cse_next_words20)
 
   uint32_t desc_tag = 0;    // monotonically increasing pass tag (30 bits used)
 
@@ -132,8 +132,8 @@ int wavelet_build(Ctx* c, uint32_t n);
 // cse.cu
 int cse_begin(Ctx* c, uint32_t n);
 struct CseWordBatch { const uint32_t* words[8]; size_t count[8]; int done; };
-// pack24: out->words[i] points at 3-byte words (BCE_EMIT_CODER: every word is below 2^24)
-int cse_advance(Ctx* c, bool resident, CseWordBatch* out, bool pack24 = false);
+// pack20: out->words[i] points at 20-bit words, two in 5 bytes (BCE_EMIT_CODER: every word is below 2^20)
+int cse_advance(Ctx* c, bool resident, CseWordBatch* out, bool pack20 = false);
 int cse_advance_buckets(Ctx* c, bce_scan_buckets* out);
 void cse_destroy(Ctx* c);
 // unbwt.cu

@@ -44,18 +44,18 @@ void ArchiveWriter::worker(int i) {
   for (;;) {
     const void* words;
     size_t count;
-    bool b24;
+    bool b20;
     {
       std::unique_lock<std::mutex> lk(mu_);
       cv_work_.wait(lk, [&] { return stop_ || job_ready_[i]; });
       if (stop_ && !job_ready_[i]) return;
       words = job_words_[i];
       count = job_count_[i];
-      b24 = job_24_[i];
+      b20 = job_20_[i];
       job_ready_[i] = false;
     }
     const auto t0 = std::chrono::steady_clock::now();
-    if (b24) streams_[i]->packed24(static_cast<const uint8_t*>(words), count);
+    if (b20) streams_[i]->packed20(static_cast<const uint8_t*>(words), count);
     else streams_[i]->packed(static_cast<const uint32_t*>(words), count);
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     {
@@ -74,14 +74,14 @@ void ArchiveWriter::begin_words(const bce_cse_words& batch) {
     if (!batch.count[i]) continue;
     job_words_[i] = batch.words[i];
     job_count_[i] = batch.count[i];
-    job_24_[i] = false;
+    job_20_[i] = false;
     job_ready_[i] = true;
     ++jobs_open_;
   }
   cv_work_.notify_all();
 }
 
-void ArchiveWriter::begin_words24(const bce_cse_words24& batch) {
+void ArchiveWriter::begin_words20(const bce_cse_words20& batch) {
   if (pool_.empty())
     for (int i = 0; i < 8; ++i) pool_.emplace_back(&ArchiveWriter::worker, this, i);
   std::lock_guard<std::mutex> lk(mu_);
@@ -89,7 +89,7 @@ void ArchiveWriter::begin_words24(const bce_cse_words24& batch) {
     if (!batch.count[i]) continue;
     job_words_[i] = batch.bytes[i];
     job_count_[i] = batch.count[i];
-    job_24_[i] = true;
+    job_20_[i] = true;
     job_ready_[i] = true;
     ++jobs_open_;
   }

@@ -23,7 +23,7 @@ class ArchiveWriter {
   // (bce.cpp:1250-1252, :1302) -- so the caller can fetch the next batch from the GPU meanwhile; wait_words
   // blocks until the batch is coded.  The batch's memory must stay valid until then.
   void begin_words(const bce_cse_words& batch);
-  void begin_words24(const bce_cse_words24& batch);               // the same words as 3 bytes each
+  void begin_words20(const bce_cse_words20& batch);               // the same words as 20 bits each
   void wait_words();
   double busy_seconds(int stream) const { return busy_[stream]; }   // time stream's coder spent coding so far
   std::vector<uint16_t> finish(uint32_t offset);
@@ -39,7 +39,7 @@ class ArchiveWriter {
   std::mutex mu_;
   std::condition_variable cv_work_, cv_done_;
   const void* job_words_[8] = {};
-  bool job_24_[8] = {};
+  bool job_20_[8] = {};
   size_t job_count_[8] = {};
   bool job_ready_[8] = {};
   int jobs_open_ = 0;

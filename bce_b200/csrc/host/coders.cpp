@@ -6,6 +6,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 
 namespace bcehost {
@@ -191,13 +192,15 @@ template <class W>
 static inline void code_packed(RangeEncoder& rc, ContextModel& model, size_t count, W word) {
   for (size_t i = 0; i < count; ++i) {
     const uint32_t w = word(i);
-    if (w & 0x800000u) {                                            // k > 31: nb uniform bits first (bce.cpp:507-510)
+    const uint32_t sym = w & 31u, ctx = (w >> 10) & 1023u;
+    uint32_t k = (w >> 5) & 31u;
+    if (k == 0) {                                                   // k > 31: nb uniform bits first (bce.cpp:507-510)
       const uint32_t w1 = word(i + 1), w2 = word(i + 2);
       i += 2;
-      const uint32_t nb = w1 & 31u, low = (w1 >> 5) | (w2 << 19);
+      const uint32_t nb = (w1 >> 5) & 31u, low = (w1 >> 10) | (w2 << 10);
+      k = w1 & 31u;
       for (uint32_t j = 0; j < nb; ++j) rc.put_uniform((low >> j) & 1u, 2);
     }
-    const uint32_t sym = w & 31u, k = (w >> 5) & 31u, ctx = (w >> 10) & 1023u;
     uint8_t* row = model.row_at(k, ctx);
     uint32_t below = sym, total = k;                                // bce.cpp:514-518
     for (uint32_t j = 0; j < sym; ++j) below += row[j];
@@ -211,9 +214,11 @@ void StreamEncoder::packed(const uint32_t* words, size_t count) {
   code_packed(rc_, model_, count, [words](size_t j) { return words[j]; });
 }
 
-void StreamEncoder::packed24(const uint8_t* b, size_t count) {
-  code_packed(rc_, model_, count, [b](size_t j) {
-    return uint32_t(b[3 * j]) | (uint32_t(b[3 * j + 1]) << 8) | (uint32_t(b[3 * j + 2]) << 16);
+void StreamEncoder::packed20(const uint8_t* b, size_t count) {
+  code_packed(rc_, model_, count, [b](size_t j) {                   // word j = bits 20 j .. of the byte string
+    uint64_t v;
+    memcpy(&v, b + 5 * (j >> 1), 8);                                // (8 bytes past the last word are readable)
+    return uint32_t(v >> (20 * (j & 1))) & 0xFFFFFu;
   });
 }
 
@@ -227,9 +232,9 @@ size_t pack_count(int mode, const uint8_t* bits_row, uint32_t sym, uint32_t k, u
     const uint32_t w = (ctx << 10) | (k << 5) | s;
     if (!nb) { out[0] = w; return 1; }
     const uint32_t low = sym & ((1u << nb) - 1u);
-    out[0] = 0x800000u | w;
-    out[1] = nb | ((low & 0x7FFFFu) << 5);
-    out[2] = low >> 19;
+    out[0] = (ctx << 10) | s;                                       // k field 0: two more words
+    out[1] = k | (nb << 5) | ((low & 0x3FFu) << 10);
+    out[2] = low >> 10;
     return 3;
   }
   while (k > uint32_t(kMaxAdaptive)) { k = (k >> 1) + (~s & 1u); s >>= 1; ++nb; }     // BCE_EMIT_SCAN

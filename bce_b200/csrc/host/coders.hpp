@@ -106,7 +106,7 @@ class StreamEncoder {
   void varint(uint32_t v);                                        // VCoder::setv
   // BCE_EMIT_CODER words (include/bce_gpu.h): context index and k > 31 halving done on the device
   void packed(const uint32_t* words, size_t count);
-  void packed24(const uint8_t* bytes, size_t count);              // the same words, 3 little-endian bytes each
+  void packed20(const uint8_t* bytes, size_t count);              // the same words, 20 bits each (bce_cse_words20)
   void finish() { rc_.finish(); }
   const std::vector<uint16_t>& words() const { return rc_.words(); }
 

@@ -64,9 +64,9 @@ int bce_archive_begin_words(bce_archive_writer* h, const bce_cse_words* batch) {
   BCE_HOST_GUARD(h->w->begin_words(*batch);)
   return BCE_GPU_OK;
 }
-int bce_archive_begin_words24(bce_archive_writer* h, const bce_cse_words24* batch) {
+int bce_archive_begin_words20(bce_archive_writer* h, const bce_cse_words20* batch) {
   if (!h || !batch) return BCE_GPU_E_ARG;
-  BCE_HOST_GUARD(h->w->begin_words24(*batch);)
+  BCE_HOST_GUARD(h->w->begin_words20(*batch);)
   return BCE_GPU_OK;
 }
 int bce_archive_wait(bce_archive_writer* h) {
@@ -174,13 +174,13 @@ int bce_compress_buffer(bce_gpu_ctx* ctx, const uint8_t* T, uint32_t n, const ui
   // Double buffering over the context's two pinned batch buffers: while the coder threads work on batch j, the
   // next call copies batch j+1 out and runs the kernels of batch j+2 (a batch stays valid until the call after
   // the next one, include/bce_gpu.h).  threads <= 1 keeps the serial form.
-  bce_cse_words24 cur, nxt;                             // 3 bytes per word over PCIe
+  bce_cse_words20 cur, nxt;                             // 20 bits per word over PCIe
   double gpu_s = 0, wait_s = 0;
   size_t nbatch = 0, nw = 0;
   auto fail = [&](int code) { bce_archive_abort(w); bce_gpu_set_emit_mode(ctx, BCE_EMIT_RAW, nullptr); return code; };
   {
     const auto a = clk::now();
-    rc = bce_gpu_cse_next_words24(ctx, &cur);
+    rc = bce_gpu_cse_next_words20(ctx, &cur);
     gpu_s += secs(a, clk::now());
     if (rc) return fail(rc);
   }
@@ -189,19 +189,19 @@ int bce_compress_buffer(bce_gpu_ctx* ctx, const uint8_t* T, uint32_t n, const ui
     for (int i = 0; i < 8; ++i) nw += cur.count[i];
     if (threads <= 1) {
       const auto a = clk::now();
-      try { w->w->begin_words24(cur); w->w->wait_words(); } catch (...) { return fail(BCE_GPU_E_NOMEM); }
+      try { w->w->begin_words20(cur); w->w->wait_words(); } catch (...) { return fail(BCE_GPU_E_NOMEM); }
       wait_s += secs(a, clk::now());
       if (cur.done) break;
       const auto b = clk::now();
-      rc = bce_gpu_cse_next_words24(ctx, &nxt);
+      rc = bce_gpu_cse_next_words20(ctx, &nxt);
       gpu_s += secs(b, clk::now());
       if (rc) return fail(rc);
     } else {
-      try { w->w->begin_words24(cur); } catch (...) { return fail(BCE_GPU_E_NOMEM); }
+      try { w->w->begin_words20(cur); } catch (...) { return fail(BCE_GPU_E_NOMEM); }
       const bool last = cur.done != 0;
       if (!last) {
         const auto a = clk::now();
-        rc = bce_gpu_cse_next_words24(ctx, &nxt);                  // coders of batch j run under this call
+        rc = bce_gpu_cse_next_words20(ctx, &nxt);                  // coders of batch j run under this call
         gpu_s += secs(a, clk::now());
       }
       const auto b = clk::now();

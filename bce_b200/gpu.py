@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "bce_gpu_stage_input", "bce_gpu_front_resident", "bce_gpu_unbwt",
     "bce_gpu_set_emit_mode", "bce_gpu_cse_next_words", "bce_gpu_set_option",
     "bce_gpu_resident_checksum", "bce_gpu_cse_next_buckets", "bce_gpu_host_alloc", "bce_gpu_host_free",
-    "bce_gpu_cse_next_words24", "bce_gpu_prefetch_input",
+    "bce_gpu_cse_next_words20", "bce_gpu_prefetch_input",
 ]
 OPT_EMIT_BATCH_BYTES, OPT_LOCAL_SORT_MIN, OPT_RESIDENT_CHECKSUM, OPT_SLOT_ENTER_NODES = 1, 2, 3, 4
 OPT_MID_ENTER_NODES, OPT_NO_NARROW_KERNELS = 5, 6
@@ -52,7 +52,7 @@ class CseWords(C.Structure):
     _fields_ = [("words", C.POINTER(C.c_uint32) * 8), ("count", C.c_size_t * 8), ("done", C.c_int)]
 
 
-class CseWords24(C.Structure):
+class CseWords20(C.Structure):
     _fields_ = [("bytes", C.POINTER(C.c_uint8) * 8), ("count", C.c_size_t * 8), ("done", C.c_int)]
 
 
@@ -120,7 +120,7 @@ def load_library() -> C.CDLL:
     lib.bce_gpu_set_scratch_limit.argtypes = [vp, C.c_size_t]
     lib.bce_gpu_set_option.argtypes = [vp, C.c_int, C.c_uint64]
     lib.bce_gpu_cse_next_buckets.argtypes = [vp, C.POINTER(ScanBuckets)]
-    lib.bce_gpu_cse_next_words24.argtypes = [vp, C.POINTER(CseWords24)]
+    lib.bce_gpu_cse_next_words20.argtypes = [vp, C.POINTER(CseWords20)]
     lib.bce_gpu_prefetch_input.argtypes = [vp, vp, u32]
     lib.bce_gpu_host_alloc.argtypes = [vp, C.c_size_t]
     lib.bce_gpu_host_alloc.restype = vp
@@ -334,7 +334,7 @@ class Frontend:
         T = _as_u8(data)
         self._check(self.lib.bce_gpu_prefetch_input(self.h, T.ctypes.data, T.size))
 
-    def compress_front_discard(self, data, words24: bool = False, prefetch_next=None):
+    def compress_front_discard(self, data, words20: bool = False, prefetch_next=None):
         """Same call sequence a consumer makes (fused front end, then batches until done) in the
         context's current emission mode; the batches are left in pinned memory (bench e2e leg).
         Returns (offset, total 32-bit words handed back)."""
@@ -344,8 +344,8 @@ class Frontend:
         self._check(self.lib.bce_gpu_compress_front(self.h, T.ctypes.data, T.size, C.byref(off), Cv))
         if prefetch_next is not None:             # the next input's upload runs beside this input's level loop
             self.prefetch_input(prefetch_next)
-        batch = CseWords24() if words24 else CseWords()
-        nxt = self.lib.bce_gpu_cse_next_words24 if words24 else self.lib.bce_gpu_cse_next_words
+        batch = CseWords20() if words20 else CseWords()
+        nxt = self.lib.bce_gpu_cse_next_words20 if words20 else self.lib.bce_gpu_cse_next_words
         total = 0
         while True:
             self._check(nxt(self.h, C.byref(batch)))
@@ -354,8 +354,8 @@ class Frontend:
                 break
         return int(off.value), total
 
-    def compress_front_words24(self, data, cfg: bytes | None = None):
-        """Fused front end, BCE_EMIT_CODER words as the 3-byte form of bce_gpu_cse_next_words24, unpacked to uint32
+    def compress_front_words20(self, data, cfg: bytes | None = None):
+        """Fused front end, BCE_EMIT_CODER words as the 20-bit form of bce_gpu_cse_next_words20, unpacked to uint32
         arrays again: (offset, C[8], 8 word arrays)."""
         T = _as_u8(data)
         self.set_emit_mode(EMIT_CODER, cfg)
@@ -364,15 +364,19 @@ class Frontend:
             Cv = (C.c_uint32 * 8)()
             self._check(self.lib.bce_gpu_compress_front(self.h, T.ctypes.data, T.size, C.byref(off), Cv))
             streams = [[] for _ in range(8)]
-            batch = CseWords24()
+            batch = CseWords20()
             while True:
-                self._check(self.lib.bce_gpu_cse_next_words24(self.h, C.byref(batch)))
+                self._check(self.lib.bce_gpu_cse_next_words20(self.h, C.byref(batch)))
                 for i in range(8):
                     cnt = int(batch.count[i])
                     if cnt:
-                        b = np.ctypeslib.as_array((C.c_uint8 * (3 * cnt)).from_address(C.addressof(batch.bytes[i].contents)))
-                        b = b.reshape(cnt, 3).astype(np.uint32)
-                        streams[i].append(b[:, 0] | (b[:, 1] << np.uint32(8)) | (b[:, 2] << np.uint32(16)))
+                        pairs = (cnt + 1) // 2
+                        b = np.ctypeslib.as_array((C.c_uint8 * (5 * pairs)).from_address(C.addressof(batch.bytes[i].contents)))
+                        b = b.reshape(pairs, 5).astype(np.uint32)
+                        w = np.empty(2 * pairs, dtype=np.uint32)
+                        w[0::2] = b[:, 0] | (b[:, 1] << np.uint32(8)) | ((b[:, 2] & np.uint32(15)) << np.uint32(16))
+                        w[1::2] = (b[:, 2] >> np.uint32(4)) | (b[:, 3] << np.uint32(4)) | (b[:, 4] << np.uint32(12))
+                        streams[i].append(w[:cnt].copy())
                 if batch.done:
                     break
         finally:

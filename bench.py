@@ -381,7 +381,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         if in_flight > 1:
             f.set_scratch_limit(ctx_limit)
         for _ in range(max(2, args.warmup // 2)):         # both pinned batch buffers get allocated here
-            f.compress_front_discard(host_in, words24=True)
+            f.compress_front_discard(host_in, words20=True)
     fe = fes[0]
     shares = [args.steps // in_flight + (1 if i < args.steps % in_flight else 0) for i in range(in_flight)]
     counts_of = [0] * in_flight
@@ -390,7 +390,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         for k in range(shares[i]):
             # a pipeline of inputs: the next step's upload (the same pinned buffer here) is started as soon as this step's
             # BWT exists and runs beside its level loop (bce_gpu_prefetch_input); the first step uploads in the open
-            _, counts_of[i] = fes[i].compress_front_discard(host_in, words24=True,
+            _, counts_of[i] = fes[i].compress_front_discard(host_in, words20=True,
                                                             prefetch_next=host_in if k + 1 < shares[i] else None)
 
     barrier()
@@ -416,7 +416,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # every rank's own e2e numbers (the job's e2e is the slowest rank's): where the time of a slow rank goes
     my_e2e = {"rank": rank, "e2e_ms_per_step": my_e2e_ms / args.steps, "ms_h2d": st_e2e["ms_h2d"], "ms_d2h": st_e2e["ms_d2h"],
               "ms_bwt_total": st_e2e["ms_bwt_total"], "ms_cse_total": st_e2e["ms_cse_total"],
-              "d2h_GBps": (int(counts) * 3 / 1e9) / (st_e2e["ms_d2h"] / 1e3) if st_e2e["ms_d2h"] > 0 else None,
+              "d2h_GBps": (int(counts) * 2.5 / 1e9) / (st_e2e["ms_d2h"] / 1e3) if st_e2e["ms_d2h"] > 0 else None,
               "h2d_GBps": (nbytes / 1e9) / (st_e2e["ms_h2d"] / 1e3) if st_e2e["ms_h2d"] > 0 else None}
     if world > 1:
         e2e_ranks = [None] * world
@@ -524,8 +524,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes,
-                    "d2h_bytes_per_step": int(counts) * 3 + 64,
-                    "emission": "BCE_EMIT_CODER words, 3 bytes each (bce_gpu_cse_next_words24)",
+                    "d2h_bytes_per_step": (int(counts) * 5 + 1) // 2 + 64,
+                    "emission": "BCE_EMIT_CODER words, 20 bits each (bce_gpu_cse_next_words20)",
                     "files_in_flight_per_gpu": in_flight,
                     "in_flight": "contexts per GPU, one whole file (upload, front end, all batches down) per step each, as "
                                  "bce_b200.batch runs a GPU: one file's copies cross PCIe under the other's kernels",
@@ -536,7 +536,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "ms_bwt_total": st_e2e["ms_bwt_total"], "ms_cse_total": st_e2e["ms_cse_total"],
                     "cse_launches": st_e2e["cse_launches"],
                     "per_rank": e2e_ranks,
-                    "aggregate_d2h_GBps_over_the_step": world * int(counts) * 3 / 1e9 / (e2e_ms / args.steps / 1e3),
+                    "aggregate_d2h_GBps_over_the_step": world * int(counts) * 2.5 / 1e9 / (e2e_ms / args.steps / 1e3),
                     "note": "ms_d2h is copy time on the copy stream; it runs under the level-loop kernels of the next "
                             "batch, so the step is max(kernels, copies) per batch, not their sum"},
             "e2e_cli": e2e_cli,

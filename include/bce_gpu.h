@@ -152,10 +152,10 @@ int bce_gpu_cse_next(bce_gpu_ctx *ctx, bce_cse_batch *out);
  *   BCE_EMIT_CODER  one word  [ctx:10 @10|k:5 @5|sym:5]  with ctx = the context index of
  *                   AdaptiveCoder::get_context (bce.cpp:671-677) for the stream's configured
  *                   context bits cfg288[stream][k]; when the reference would halve k > 31
- *                   (bce.cpp:507-510) nb times: [1 @23|ctx|k'|sym'] followed by two words
- *                   [low[0..19) @5|nb:5] and [low >> 19] with the nb low bits of the symbol (coded
- *                   uniformly, LSB first).  Every word is below 2^24: bce_gpu_cse_next_words24 hands
- *                   the same words back as 3 bytes each (a quarter less over PCIe)
+ *                   (bce.cpp:507-510) nb times: [ctx|0|sym'] -- k field 0, a count's k is at least 2 --
+ *                   followed by two words [low[0..10) @10|nb:5 @5|k':5] and [low >> 10] with the nb low
+ *                   bits of the symbol (coded uniformly, LSB first).  Every word is below 2^20:
+ *                   bce_gpu_cse_next_words20 hands the same words back as 20 bits each (3/8 less over PCIe)
  *   BCE_EMIT_SCAN   one word  [esc|nb:5 @26|q2:8 @18|q1:8 @10|k:5 @5|sym:5], q = (c << 8) / cs,
  *                   halving rule of ScanCoder::set (bce.cpp:737-744)
  * set_emit_mode applies to the following cse_begin / compress_front calls of the context.
@@ -168,14 +168,16 @@ typedef struct bce_cse_words {
 } bce_cse_words;
 int bce_gpu_set_emit_mode(bce_gpu_ctx *ctx, int mode, const uint8_t *cfg288);
 int bce_gpu_cse_next_words(bce_gpu_ctx *ctx, bce_cse_words *out);
-/* BCE_EMIT_CODER only: the batch as 3 little-endian bytes per word (word j of stream i =
- * bytes[i][3j] | bytes[i][3j+1] << 8 | bytes[i][3j+2] << 16), packed on the device before the copy. */
-typedef struct bce_cse_words24 {
+/* BCE_EMIT_CODER only: the batch as 20 bits per word, packed on the device before the copy: word j of stream i
+ * is bits 20 j .. 20 j + 19 of the little-endian bit string bytes[i] (two words in 5 bytes; with o = 5 (j / 2):
+ * even j = b[o] | b[o+1] << 8 | (b[o+2] & 15) << 16, odd j = b[o+2] >> 4 | b[o+3] << 4 | b[o+4] << 12).
+ * At least 8 bytes past the last word are readable. */
+typedef struct bce_cse_words20 {
   const uint8_t *bytes[8];    /* pinned host memory, valid as bce_cse_batch: until the call after the next */
-  size_t count[8];            /* words (3 bytes each) */
+  size_t count[8];            /* words (20 bits each) */
   int done;
-} bce_cse_words24;
-int bce_gpu_cse_next_words24(bce_gpu_ctx *ctx, bce_cse_words24 *out);
+} bce_cse_words20;
+int bce_gpu_cse_next_words20(bce_gpu_ctx *ctx, bce_cse_words20 *out);
 
 /* ---- `bce -s`: counts bucketed on the device ------------------------------------------------
  * ScanCoder::set (bce.cpp:737-744) appends every symbol to stat_[k][(q2 << 16) | q1]; its flush

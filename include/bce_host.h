@@ -32,7 +32,7 @@ int bce_archive_feed_words(bce_archive_writer *w, const bce_cse_words *batch, in
  * reference forks its eight coders inside the level loop, bce.cpp:1250-1252, :1302); wait blocks until the
  * batch is coded.  The batch's memory must stay valid until then; one batch in flight at a time. */
 int bce_archive_begin_words(bce_archive_writer *w, const bce_cse_words *batch);
-int bce_archive_begin_words24(bce_archive_writer *w, const bce_cse_words24 *batch);   /* bce_gpu_cse_next_words24 batches */
+int bce_archive_begin_words20(bce_archive_writer *w, const bce_cse_words20 *batch);   /* bce_gpu_cse_next_words20 batches */
 int bce_archive_wait(bce_archive_writer *w);
 /* flush, header (n, offset, sizes), concatenate; *words is malloc'd (bce_host_free). */
 int bce_archive_finish(bce_archive_writer *w, uint32_t offset, uint16_t **words, size_t *nwords);

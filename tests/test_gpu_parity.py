@@ -186,25 +186,27 @@ def test_prefetched_input_is_the_input(frontend):
             lib.bce_gpu_host_free(h, p)
 
 
-def test_three_byte_words_are_the_same_words(frontend):
-    """bce_gpu_cse_next_words24: the CODER words of a batch as 3 bytes each (packed on the device before the copy),
-    on inputs with many k > 31 counts (three-word escapes) and over several batches."""
+def test_twenty_bit_words_are_the_same_words(frontend):
+    """bce_gpu_cse_next_words20: the CODER words of a batch as 20 bits each (packed on the device before the copy),
+    on inputs with many k > 31 counts (three-word escapes, k field 0) and over several batches."""
     from bce_b200 import synth
     from bce_b200.gpu import EMIT_CODER, OPT_EMIT_BATCH_BYTES
     cases = [synth.generate("mixed-binary", (1 << 20) + 77, 4).tobytes(), synth.generate("enwik-shaped", 400_000, 9).tobytes(),
              b"a" * 999 + b"b", b"hello world, hello world! the quick brown fox jumps over the lazy dog"]
+    seen_escape = False
     for data in cases:
         _, Cv, words = frontend.compress_front_words(data, EMIT_CODER)
+        seen_escape |= any((((w >> 5) & 31) == 0).any() for w in words if w.size)
         frontend.set_option(OPT_EMIT_BATCH_BYTES, 1 << 20)
         try:
-            _, Cv2, words24 = frontend.compress_front_words24(data)
+            _, Cv2, words20 = frontend.compress_front_words20(data)
         finally:
             frontend.set_option(OPT_EMIT_BATCH_BYTES, 0)
         assert Cv2 == Cv
         for i in range(8):
-            assert first_diff(words24[i], words[i]) is None, i
-            assert not words[i].size or int(words[i].max()) < (1 << 24)
-    assert any((w & 0x800000).any() for w in words) or True
+            assert first_diff(words20[i], words[i]) is None, i
+            assert not words[i].size or int(words[i].max()) < (1 << 20)
+    assert seen_escape, "no k > 31 count in any case"
 
 
 def test_slot_layout_forced_on_small_inputs(frontend):

@@ -187,10 +187,12 @@ void StreamEncoder::count(uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2, ui
   ContextModel::bump(row, k, sym);
 }
 
-// One packed count (include/bce_gpu.h, BCE_EMIT_CODER): W(j) reads word j of the batch.
+// Packed counts (include/bce_gpu.h, BCE_EMIT_CODER): W(j) reads word j; codes the counts that START in [first, count)
+// and returns the index behind the last word used (a k > 31 count at the end reaches up to two words past `count`).
 template <class W>
-static inline void code_packed(RangeEncoder& rc, ContextModel& model, size_t count, W word) {
-  for (size_t i = 0; i < count; ++i) {
+static inline size_t code_packed(RangeEncoder& rc, ContextModel& model, size_t first, size_t count, W word) {
+  size_t i = first;
+  for (; i < count; ++i) {
     const uint32_t w = word(i);
     const uint32_t sym = w & 31u, ctx = (w >> 10) & 1023u;
     uint32_t k = (w >> 5) & 31u;
@@ -208,18 +210,32 @@ static inline void code_packed(RangeEncoder& rc, ContextModel& model, size_t cou
     rc.put(below, uint32_t(row[sym]) + 1, total);
     ContextModel::bump(row, k, sym);
   }
+  return i;
 }
 
 void StreamEncoder::packed(const uint32_t* words, size_t count) {
-  code_packed(rc_, model_, count, [words](size_t j) { return words[j]; });
+  code_packed(rc_, model_, 0, count, [words](size_t j) { return words[j]; });
 }
 
+// 20-bit words (bce_cse_words20): unpacked a block at a time into aligned words -- one 8-byte load per pair in a
+// loop of its own -- so that the coder's loop reads what it reads in the 32-bit form.
 void StreamEncoder::packed20(const uint8_t* b, size_t count) {
-  code_packed(rc_, model_, count, [b](size_t j) {                   // word j = bits 20 j .. of the byte string
-    uint64_t v;
-    memcpy(&v, b + 5 * (j >> 1), 8);                                // (8 bytes past the last word are readable)
-    return uint32_t(v >> (20 * (j & 1))) & 0xFFFFFu;
-  });
+  constexpr size_t BLK = 4096;                                      // even: a block starts on a 5-byte group
+  uint32_t buf[BLK + 4];
+  size_t skip = 0;                                                  // words of this block already used by the last count of the previous one
+  for (size_t base = 0; base < count; base += BLK) {
+    const size_t n = std::min(BLK, count - base), m = std::min(n + 2, count - base);
+    const uint8_t* p = b + 5 * (base >> 1);
+    for (size_t t = 0; t < m; t += 2, p += 5) {                     // (8 bytes past the last word are readable)
+      uint64_t v;
+      memcpy(&v, p, 8);
+      buf[t] = uint32_t(v) & 0xFFFFFu;
+      buf[t + 1] = uint32_t(v >> 20) & 0xFFFFFu;
+    }
+    const uint32_t* w = buf;
+    const size_t end = code_packed(rc_, model_, skip, n, [w](size_t j) { return w[j]; });
+    skip = end - n;
+  }
 }
 
 size_t pack_count(int mode, const uint8_t* bits_row, uint32_t sym, uint32_t k, uint32_t c1, uint32_t c2,

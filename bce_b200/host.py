@@ -129,6 +129,61 @@ def encode_archive_words(Cvals, word_streams, n: int, offset: int, cfg: bytes | 
     return out
 
 
+def pack20(words) -> np.ndarray:
+    """uint32 words below 2^20 -> the byte string of bce_cse_words20 (word j at bit 20 j, 16 readable bytes of slack)."""
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    pairs = (w.shape[0] + 1) // 2
+    a = np.zeros(2 * pairs, dtype=np.uint64)
+    a[:w.shape[0]] = w
+    v = a[0::2] | (a[1::2] << np.uint64(20))
+    out = np.zeros(pairs * 5 + 16, dtype=np.uint8)
+    for k in range(5):
+        out[k:pairs * 5:5] = ((v >> np.uint64(8 * k)) & np.uint64(255)).astype(np.uint8)
+    return out
+
+
+def encode_archive_words20(Cvals, word_streams, n: int, offset: int, cfg: bytes | None = None, pieces: int = 1) -> bytes:
+    """Archive writer over BCE_EMIT_CODER word streams handed over as 20-bit words (bce_archive_begin_words20 /
+    bce_archive_wait), in `pieces` batches per stream cut at count boundaries."""
+    from .gpu import CseWords20
+    lib = load_library()
+    lib.bce_archive_begin_words20.argtypes = [C.c_void_p, C.POINTER(CseWords20)]
+    Cv = (C.c_uint32 * 8)(*Cvals)
+    cfgbuf = np.frombuffer(cfg, dtype=np.uint8) if cfg is not None else None
+    w = lib.bce_archive_begin(n, Cv, cfgbuf.ctypes.data if cfgbuf is not None else None)
+    cuts = []
+    for s in word_streams:                                   # a k > 31 count is three words: never cut inside one
+        s = np.asarray(s, dtype=np.uint32)
+        starts = []
+        i = 0
+        esc = ((s >> np.uint32(5)) & np.uint32(31)) == 0
+        while i < s.shape[0]:
+            starts.append(i)
+            i += 3 if esc[i] else 1
+        starts.append(s.shape[0])
+        cuts.append([starts[(len(starts) - 1) * p // pieces] for p in range(pieces)] + [s.shape[0]])
+    for p in range(pieces):
+        b = CseWords20()
+        keep = []
+        for i, s in enumerate(word_streams):
+            part = np.asarray(s, dtype=np.uint32)[cuts[i][p]:cuts[i][p + 1]]
+            keep.append(pack20(part))
+            b.count[i] = part.shape[0]
+            if part.shape[0]:
+                b.bytes[i] = C.cast(keep[-1].ctypes.data, C.POINTER(C.c_uint8))
+        b.done = 1 if p == pieces - 1 else 0
+        assert lib.bce_archive_begin_words20(w, C.byref(b)) == 0
+        assert lib.bce_archive_wait(w) == 0
+    words = C.c_void_p()
+    nw = C.c_size_t()
+    rc = lib.bce_archive_finish(w, offset, C.byref(words), C.byref(nw))
+    if rc != 0:
+        raise RuntimeError(f"bce_archive_finish failed: {rc}")
+    out = C.string_at(words.value, nw.value * 2)
+    lib.bce_host_free(words)
+    return out
+
+
 def scan_config_words(word_streams) -> bytes:
     lib = load_library()
     s = lib.bce_scan_begin()

@@ -158,6 +158,31 @@ def test_packed_wide_ranges():
     assert host.encode_archive_words(Cv, words, 2000, 11) == oracle.encode_archive(Cv, streams, 2000, 11)
 
 
+def test_twenty_bit_words_code_the_same_archive():
+    """bce_cse_words20 (two words in 5 bytes) through the overlapped writer: many k > 31 counts (three-word escapes, k
+    field 0), streams longer than the unpacker's 4096-word blocks so that escapes straddle block ends, several batches."""
+    import numpy as np
+    from bce_b200.gpu import EMIT_CODER
+    rng = np.random.default_rng(6)
+    streams = []
+    for i in range(8):
+        m = 9000 + 501 * i
+        wide = rng.random(m) < 0.3                                   # a third of the counts have k > 31
+        k = np.where(wide, rng.integers(32, 1 << 20, size=m), rng.integers(2, 32, size=m)).astype(np.uint32)
+        s = (rng.integers(0, 1 << 30, size=m, dtype=np.uint32) % k).astype(np.uint32)
+        cs = rng.integers(2, 1 << 31, size=m, dtype=np.uint32)
+        c1 = (rng.integers(0, 1 << 31, size=m, dtype=np.uint32) % cs).astype(np.uint32)
+        c2 = (rng.integers(0, 1 << 31, size=m, dtype=np.uint32) % cs).astype(np.uint32)
+        streams.append(np.stack([s, k, c1, c2, cs], axis=1).astype(np.uint32))
+    Cv = [7] * 8
+    words = host.pack_counts(EMIT_CODER, streams)
+    assert all(int(w.max()) < (1 << 20) for w in words)
+    want = oracle.encode_archive(Cv, streams, 2000, 11)
+    assert host.encode_archive_words(Cv, words, 2000, 11) == want
+    for pieces in (1, 3):
+        assert host.encode_archive_words20(Cv, words, 2000, 11, pieces=pieces) == want, pieces
+
+
 @pytest.mark.parametrize("name,data,primitive", [c for c in CASES if c[2]], ids=[c[0] for c in CASES if c[2]])
 def test_host_decoder_low_memory_path(name, data, primitive):
     """`bce -ds`: header + 8 adaptive decoders + the level loop in decode mode + serial inverse,

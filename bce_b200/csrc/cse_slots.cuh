@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) cse_slots_to_flat_kernel(CseArgs a, SlotA
       }
       if (g < v.n) {
         const uint32_t local = g - P[lo];
-        const uint32_t from = (lo < v.sz ? v.zoff + lo * SL_CH : v.ooff + (lo - v.sz) * SL_CH) + local;
+        const uint32_t from = v.zoff + lo * SL_CH + local;            // (the O-slots follow the Z-slots: ooff = zoff + sz * SL_CH)
         const uint32_t to = g < v.nz ? g : a.cap - 1u - (g - v.nz);
         a.fs[par][l][to] = sa.ns[par][from];
         a.fa[par][l][to] = sa.na[par][from];
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(SL_THREADS, SL_MINB) cse_slots_kernel(CseArgs 
         for (int j = 0; j < SL_ITEMS; ++j) {
           ns[j] = na[j] = nb[j] = 0;
           if (g[j] < gend) {
-            const uint32_t at = (c[j] < v.sz ? v.zoff + c[j] * SL_CH : v.ooff + (c[j] - v.sz) * SL_CH) + (g[j] - pc[j]);
+            const uint32_t at = v.zoff + c[j] * SL_CH + (g[j] - pc[j]);      // (the O-slots follow the Z-slots: ooff = zoff + sz * SL_CH)
             ns[j] = __ldcg(sa.ns[cur] + at);
             na[j] = __ldcg(sa.na[cur] + at);
             nb[j] = __ldcg(sa.nb[cur] + at);

@@ -160,18 +160,19 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
   // is the slot after the warp's last one a head (or the end)?
   const bool after_is_head = (wbase + RR_WCHUNK >= a.m) ||
                              (key_after != __shfl_sync(0xffffffffu, key[RR_ROWS - 1], 31));
-  // lone = a group of one: head whose successor is a head (or the end of the working set)
+  // lone = a group of one: head whose successor is a head (or the end of the working set).  H[k] is the same in all
+  // lanes, so the three masks of a row are a handful of bit operations, no further ballots:
+  //   L lone slots, S survivors (tied slots), SH surviving heads
   auto masks = [&](int k, uint32_t& S, uint32_t& SH, uint32_t& L) {
-    const uint32_t q = wbase + k * 32 + lane;
-    const bool in = q < a.m;
-    const bool head = (H[k] >> lane) & 1u;
-    const bool nh = (q + 1 >= a.m) ? true
-                  : lane < 31 ? ((H[k] >> (lane + 1)) & 1u)
-                  : k + 1 < RR_ROWS ? (H[k + 1 < RR_ROWS ? k + 1 : k] & 1u) : after_is_head;
-    const bool lone = head && nh;
-    L = __ballot_sync(0xffffffffu, in && lone);
-    S = __ballot_sync(0xffffffffu, in && !lone);
-    SH = __ballot_sync(0xffffffffu, in && head && !lone);
+    const uint32_t rowbase = wbase + k * 32;
+    const uint32_t valid = rowbase >= a.m ? 0u : a.m - rowbase;                   // slots of the row below m
+    const uint32_t in_mask = valid >= 32u ? 0xFFFFFFFFu : (1u << valid) - 1u;
+    const uint32_t next_first = k + 1 < RR_ROWS ? (H[k + 1 < RR_ROWS ? k + 1 : k] & 1u) : (after_is_head ? 1u : 0u);
+    uint32_t nh = (H[k] >> 1) | (next_first << 31);                               // the slot behind is a head ...
+    if (valid <= 32u) nh |= valid ? ~((1u << (valid - 1u)) - 1u) : 0xFFFFFFFFu;   // ... or does not exist
+    L = H[k] & nh & in_mask;
+    S = in_mask & ~L;
+    SH = H[k] & ~L;
   };
   uint32_t wsurv = 0, wshead = 0, whead = 0;          // this warp's survivors, surviving heads, (slot + 1) of its last head
 #pragma unroll

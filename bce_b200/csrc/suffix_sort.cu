@@ -77,7 +77,7 @@ constexpr int RR_WARPS = RR_THREADS / 32;
 #endif
 constexpr int RR_ROWS = BCE_RR_ROWS;                // rows of 32 consecutive slots per warp
 constexpr int RR_WCHUNK = 32 * RR_ROWS;             // slots per warp
-constexpr int RR_TILE = RR_WARPS * RR_WCHUNK;       // 2048 slots per tile
+constexpr int RR_TILE = RR_WARPS * RR_WCHUNK;       // 4096 slots per tile
 
 struct RerankArgs {
   const uint64_t* key;      // sorted keys of the working set
@@ -107,6 +107,13 @@ struct RerankArgs {
 // ballot masks of the rows (one 32-bit word per row, the same in all lanes) with popc / clz.
 // (A first version gave every thread 8-16 consecutive slots: ncu showed 22 sectors per store request
 // and the L1 as the busiest unit.)
+// timing experiments (parts of the kernel switched off, results wrong) exist in experiment builds only
+#ifdef BCE_GPU_EXPERIMENTS
+#define RR_DBG(a) ((a).dbg)
+#else
+#define RR_DBG(a) 0u
+#endif
+
 __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
   __shared__ uint32_t s_whead[RR_WARPS], s_wsurv[RR_WARPS], s_wshead[RR_WARPS];
   __shared__ uint32_t s_tile;
@@ -226,11 +233,11 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
       // slots of one group are consecutive in SA, so the head's SA position is sap - distance
       const uint32_t rank = sap[k] - (q - (my_head - 1));
       // SA is final for a slot once its group is a single rotation; tied slots come back next round
-      if (((L >> lane) & 1u) && !(a.dbg & 2u)) a.sa[sap[k]] = idx[k];
+      if (((L >> lane) & 1u) && !(RR_DBG(a) & 2u)) a.sa[sap[k]] = idx[k];
       if (binned) s_stage[s_bstart[(idx[k] >> a.part_shift) & 255u] + ((bpos[k / 2] >> ((k & 1) * 16)) & 0xFFFFu)] = (uint64_t(idx[k]) << 32) | rank;
       else if (a.pairs) a.pairs[q] = (uint64_t(idx[k]) << 32) | rank;
-      else if (!(a.dbg & 1u)) a.rnk[idx[k]] = rank;
-      if (((S >> lane) & 1u) && !(a.dbg & 4u)) {
+      else if (!(RR_DBG(a) & 1u)) a.rnk[idx[k]] = rank;
+      if (((S >> lane) & 1u) && !(RR_DBG(a) & 4u)) {
         const uint32_t at = out_at + __popc(S & lanemask_lt());
         a.idx_out[at] = idx[k];
         a.sapos_out[at] = sap[k];

@@ -78,6 +78,10 @@ constexpr int RR_WARPS = RR_THREADS / 32;
 constexpr int RR_ROWS = BCE_RR_ROWS;                // rows of 32 consecutive slots per warp
 constexpr int RR_WCHUNK = 32 * RR_ROWS;             // slots per warp
 constexpr int RR_TILE = RR_WARPS * RR_WCHUNK;       // 4096 slots per tile
+#ifndef BCE_RR_LOOKBACK
+#define BCE_RR_LOOKBACK 4
+#endif
+constexpr int RR_LOOKBACK = BCE_RR_LOOKBACK;        // descriptors x 32 fetched per step of the two sum scans
 
 struct RerankArgs {
   const uint64_t* key;      // sorted keys of the working set
@@ -212,8 +216,8 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(RerankArgs a) {
     uint64_t* d = a.desc + size_t(warp) * a.tiles;
     uint32_t v;
     if (warp == 0) v = lookback_warp_max(d, tile, 0u, a.tag, tile_head, a.err);
-    else if (warp == 1) v = lookback_warp(d, tile, 0u, a.tag, tile_surv, a.err);
-    else v = lookback_warp(d, tile, 0u, a.tag, tile_shead, a.err);
+    else if (warp == 1) v = lookback_warp_wide<RR_LOOKBACK>(d, tile, 0u, a.tag, tile_surv, a.err);
+    else v = lookback_warp_wide<RR_LOOKBACK>(d, tile, 0u, a.tag, tile_shead, a.err);
     if (lane == 0) s_carry[warp] = v;
   }
   __syncthreads();
